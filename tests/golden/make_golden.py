@@ -1,0 +1,186 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference
+(/root/reference/GAT/{layers,models,create_batch}.py, imported, never copied) on seeded inputs.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+The committed *.npz files hold inputs, parameters, dropout masks, outputs, gradients and the
+reference's .data side effects; tests/test_oracle_golden.py pins oracle/ against them and the
+-m gpu tests pin the CUDA path against them.
+"""
+import os
+import sys
+import types
+import copy
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/GAT")
+
+# create_batch.py imports nltk (absent here) only for an unrelated tokenizer.
+_nltk = types.ModuleType("nltk"); _tok = types.ModuleType("nltk.tokenize")
+_tok.word_tokenize = lambda s: s.split(); _nltk.tokenize = _tok
+sys.modules.setdefault("nltk", _nltk); sys.modules.setdefault("nltk.tokenize", _tok)
+
+import layers as ref_layers          # noqa: E402
+import models as ref_models          # noqa: E402
+import create_batch as ref_batch     # noqa: E402
+from recon_b200.synth import make_kg, make_triples   # noqa: E402
+
+ref_layers.CUDA = ref_models.CUDA = False
+
+
+class FixedMask(torch.nn.Module):
+    """Stands in for an nn.Dropout instance of the reference so that a known mask is applied."""
+
+    def __init__(self, mask):
+        super().__init__()
+        self.mask = mask
+
+    def forward(self, x):
+        return x * self.mask.to(x.dtype)
+
+
+def drop_mask(shape, p, gen):
+    return (torch.rand(shape, generator=gen) >= p).float() / (1.0 - p)
+
+
+def model_case(name, n, e, r, in_dim, out_dim, nheads, alpha_zipf, n_nhop, batch, p_drop, seed,
+               batch_test=False):
+    edge, etype, nhop = make_kg(n, e, r, alpha_zipf, n_nhop, seed)
+    torch.manual_seed(seed)
+    ent0 = torch.randn(n, in_dim); rel0 = torch.randn(r, in_dim)
+    model = ref_models.SpKBGATModified(ent0.clone(), rel0.clone(), [out_dim, 2 * out_dim], [out_dim, 2 * out_dim],
+                                       p_drop, 0.2, [nheads, nheads], None)
+    gen = torch.Generator().manual_seed(seed + 1)
+    etot = e + n_nhop
+    masks = {}
+    if p_drop > 0:
+        masks["att"] = torch.stack([drop_mask((etot,), p_drop, gen) for _ in range(nheads)])
+        masks["out"] = drop_mask((etot,), p_drop, gen)
+        masks["x"] = drop_mask((n, out_dim * nheads), p_drop, gen)
+        for i in range(nheads):
+            getattr(model.sparse_gat_1, f"attention_{i}").dropout = FixedMask(masks["att"][i])
+        model.sparse_gat_1.out_att.dropout = FixedMask(masks["out"])
+        model.sparse_gat_1.dropout_layer = FixedMask(masks["x"])
+    params0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    g_ent = torch.randn(n, out_dim * nheads, generator=gen)
+    g_rel = torch.randn(r, out_dim * nheads, generator=gen)
+    batch_entities = torch.as_tensor(batch, dtype=torch.int64)
+    out = {"edge": edge, "edge_type": etype, "nhop": nhop, "batch_entities": batch_entities,
+           "g_ent": g_ent, "g_rel": g_rel, "alpha": np.float32(0.2), "p_drop": np.float32(p_drop)}
+    for k, v in masks.items():
+        out["mask." + k] = v
+    for k, v in params0.items():
+        out["param." + k] = v
+
+    def run(m):
+        if batch_test:
+            ent_in = torch.randn(n, in_dim, generator=torch.Generator().manual_seed(seed + 2)).to(
+                next(m.parameters()).dtype)
+            o_e, o_r, msk = m.batch_test(None, batch_entities, (edge, etype), nhop, ent_in)
+            return o_e, o_r, msk, ent_in
+        o_e, o_r, msk = m(None, batch_entities, (edge, etype), nhop)
+        return o_e, o_r, msk, None
+
+    m64 = copy.deepcopy(model).double()
+    for tag, m, ge, gr in (("f32", model, g_ent, g_rel), ("f64", m64, g_ent.double(), g_rel.double())):
+        o_e, o_r, msk, ent_in = run(m)
+        loss = (o_e * ge).sum() + (o_r * gr).sum()
+        loss.backward()
+        out[f"{tag}.out_entity"] = o_e.detach(); out[f"{tag}.out_relation"] = o_r.detach()
+        out[f"{tag}.mask"] = msk
+        if ent_in is not None and tag == "f32":
+            out["entity_in"] = ent_in
+        for k, prm in m.named_parameters():
+            if prm.grad is not None:
+                out[f"{tag}.grad.{k}"] = prm.grad.detach()
+        for k, v in m.state_dict().items():          # side effects (models.py:160-161,181-183)
+            if k in ("entity_embeddings", "final_entity_embeddings", "final_relation_embeddings"):
+                out[f"{tag}.after.{k}"] = v.detach().clone()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v) for k, v in out.items()})
+    print(name, "ok", {k: tuple(np.asarray(v).shape) for k, v in out.items() if k.startswith("f32.out")})
+
+
+def layer_case(name, n, e, e2, f_in, d, rd, concat, seed):
+    """SpGraphAttentionLayer stand-alone, per-edge embeddings given (layers.py:111)."""
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    layer = ref_layers.SpGraphAttentionLayer(n, f_in, d, rd, 0.0, 0.2, concat)
+    x = torch.randn(n, f_in, generator=gen, requires_grad=True)
+    edge = torch.randint(0, n, (2, e), generator=gen)
+    edge[0, : e // 4] = 3                                   # one heavier row, a few empty rows remain
+    emb = torch.randn(e, rd, generator=gen, requires_grad=True)
+    edge2 = torch.randint(0, n, (2, e2), generator=gen) if e2 else torch.tensor([])
+    emb2 = torch.randn(e2, rd, generator=gen, requires_grad=True) if e2 else torch.tensor([])
+    g = torch.randn(n, d, generator=gen)
+    out = layer(x, edge, emb, edge2, emb2)
+    (out * g).sum().backward()
+    res = {"x": x.detach(), "edge": edge, "edge_embed": emb.detach(), "edge_nhop": edge2,
+           "edge_embed_nhop": emb2.detach(), "g": g, "a": layer.a.detach(), "a_2": layer.a_2.detach(),
+           "concat": np.int32(concat), "out": out.detach(), "grad.x": x.grad, "grad.edge_embed": emb.grad,
+           "grad.a": layer.a.grad, "grad.a_2": layer.a_2.grad}
+    if e2:
+        res["grad.edge_embed_nhop"] = emb2.grad
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v) for k, v in res.items()})
+    print(name, "ok")
+
+
+def spmm_case(name, n, e, f, seed):
+    """SpecialSpmmFunctionFinal.apply stand-alone (layers.py:51-79)."""
+    gen = torch.Generator().manual_seed(seed)
+    edge = torch.randint(0, n, (2, e), generator=gen)
+    w = torch.randn(e, f, generator=gen, requires_grad=True)
+    g = torch.randn(n, f, generator=gen)
+    out = ref_layers.SpecialSpmmFunctionFinal.apply(edge, w, n, e, f)
+    (out * g).sum().backward()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), edge=edge.numpy(), w=w.detach().numpy(), g=g.numpy(),
+                        out=out.detach().numpy(), grad_w=w.grad.numpy())
+    print(name, "ok")
+
+
+def edges_case(name, n, t, r, seed, batch_size, partial=False):
+    """Corpus.get_graph / bfs / get_batch_adj_data / get_batch_nhop_neighbors_all on random triples."""
+    triples = make_triples(n, t, r, seed)
+    rows = triples[:, 2].tolist(); cols = triples[:, 0].tolist(); data = triples[:, 1].tolist()
+    c = ref_batch.Corpus.__new__(ref_batch.Corpus)
+    c.train_adj_matrix = (torch.LongTensor([rows, cols]), torch.LongTensor(data))     # create_batch.py:28-31
+    c.graph = c.get_graph(Train=True)
+    c.node_neighbors_1hop = c.get_further_neighbors(nbd_size=1, Train=True)
+    c.node_neighbors_2hop = c.get_further_neighbors(nbd_size=2, Train=True)
+    gen = torch.Generator().manual_seed(seed + 7)
+    batch = torch.randperm(n, generator=gen)[:batch_size].tolist()
+    (adj_idx, adj_val), ents = c.get_batch_adj_data(None, unique_entities_train=batch, start_idx=0, end_idx=len(batch))
+    args = types.SimpleNamespace(partial_2hop=partial)
+    nhop = c.get_batch_nhop_neighbors_all(args, batch, c.node_neighbors_2hop)
+    all_src = list(range(n))
+    (fadj_idx, fadj_val), _ = c.get_batch_adj_data(None, unique_entities_train=all_src, start_idx=0, end_idx=n)
+    fnhop = c.get_batch_nhop_neighbors_all(args, all_src, c.node_neighbors_2hop)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), triples=triples.numpy(), batch=np.asarray(batch),
+                        adj_idx=adj_idx.numpy(), adj_val=adj_val.numpy(), nhop=nhop.reshape(-1, 4),
+                        full_adj_idx=fadj_idx.numpy(), full_adj_val=fadj_val.numpy(), full_nhop=fnhop.reshape(-1, 4),
+                        partial=np.int32(partial))
+    print(name, "ok", adj_idx.shape, nhop.shape, fnhop.shape)
+
+
+if __name__ == "__main__":
+    import warnings
+    warnings.filterwarnings("ignore")
+    model_case("model_small_uniform", 60, 300, 7, 12, 8, 2, None, 0, [3, 5, 5, 17, 40, 41], 0.0, 0)
+    model_case("model_small_zipf_nhop", 80, 400, 9, 12, 8, 2, 1.1, 150, list(range(80)), 0.0, 1)
+    model_case("model_small_dropmask", 70, 350, 5, 16, 12, 2, 1.5, 120, list(range(0, 70, 2)), 0.3, 2)
+    model_case("model_refdims", 150, 1200, 11, 50, 100, 2, 1.1, 300, list(range(150)), 0.0, 3)
+    model_case("model_batch_test", 60, 300, 7, 12, 8, 2, None, 80, list(range(30)), 0.0, 4, batch_test=True)
+    model_case("model_3heads", 50, 260, 6, 10, 4, 3, 2.0, 0, list(range(50)), 0.0, 5)
+    layer_case("layer_concat", 40, 200, 0, 10, 8, 6, True, 10)
+    layer_case("layer_noconcat_nhop", 40, 200, 60, 12, 16, 12, False, 11)
+    spmm_case("spmm_f1", 30, 200, 1, 20)
+    spmm_case("spmm_f7", 30, 200, 7, 21)
+    edges_case("edges_a", 40, 160, 5, 30, 12)
+    edges_case("edges_b", 25, 200, 3, 31, 25)
+    edges_case("edges_partial", 40, 160, 5, 32, 15, partial=True)
+    # the hand-checked toy KG of SURVEY.md 3.4
+    toy = np.array([(0, 5, 1), (0, 6, 1), (0, 7, 2), (1, 8, 3), (2, 9, 3), (2, 4, 2), (3, 1, 4), (1, 2, 0)])
+    np.savez_compressed(os.path.join(HERE, "edges_toy.npz"), triples=toy)
