@@ -1,0 +1,144 @@
+/* libspkbgat -- C ABI of the B200-native SpKBGAT hot path (sm_100a).
+ *
+ * The reference (ansonb/RECON) has no FFI for this path: its boundary is the Python nn.Module /
+ * autograd.Function surface of GAT/layers.py and GAT/models.py. These entry points are what a
+ * binding for that path calls instead of the ATen ops listed beside each one. All pointers are raw
+ * CUDA device pointers (caller-owned, 16-byte aligned, fp32 / int32 unless stated); the library
+ * never allocates or frees device memory and keeps no pointer after a call returns. Every call
+ * enqueues on `stream` and returns 0 on success, else a non-zero code with the text available from
+ * spk_last_error() (thread-local). See INTEGRATION.md for the ctypes binding the reference-side
+ * Python uses.
+ *
+ * Projected-table row format ("P~ rows", width = spk_geom.width floats, a multiple of 8):
+ *     [ n_heads * d_pad projection floats | n_heads score scalars q | zero pad ]
+ * d_pad = d_head rounded up to 4; n_heads <= 4 per launch (the host loops over head groups).
+ */
+#ifndef SPKBGAT_H
+#define SPKBGAT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* spk_stream_t;              /* cudaStream_t */
+
+#define SPK_ABI_VERSION 1
+int spk_abi_version(void);
+const char* spk_last_error(void);
+int64_t spk_launch_count(void);          /* kernels launched through this library so far */
+
+typedef struct {
+    int32_t n_heads;   /* H  (1..4) */
+    int32_t d_head;    /* D  out_features per head (GAT/layers.py:92 out_features) */
+    int32_t d_pad;     /* Dp */
+    int32_t width;     /* Wd */
+} spk_geom;
+
+/* Segments longer than hub_thresh are processed as chunks (tasks) with partials summed in task
+ * order: deterministic handling of power-law hub rows. n_tasks == 0 disables it. */
+typedef struct {
+    const int32_t* task_seg;
+    const int32_t* task_beg;
+    const int32_t* task_end;
+    const int32_t* hub_seg;
+    const int32_t* hub_task_ptr;
+    float* partial;            /* [n_tasks, ldpart] scratch */
+    int64_t ldpart;            /* fwd: width+8 ; bwd_rows: 8 ; seg_gather: width */
+    int32_t n_tasks;
+    int32_t n_hubs;
+    int32_t hub_thresh;
+    int32_t reserved;
+} spk_hub_tasks;
+
+/* ---- K0: edge construction (replaces the Python/ATen edge prep of GAT/models.py:141-148,
+ *      GAT/layers.py:124-127 and the coalesce inside SpecialSpmmFunctionFinal, layers.py:56-58) ---- */
+int spk_edges_concat(const int64_t* edge /*[2,E1]*/, int64_t e1, const int64_t* edge_type /*[E1]*/,
+                     const int64_t* nhop /*[E2,4] = s,r1,r2,t*/, int64_t e2,
+                     int32_t* row, int32_t* col, int32_t* t1, int32_t* t2 /*null if e2==0*/,
+                     int64_t n_nodes, int64_t n_rel, int32_t* err_flag, spk_stream_t stream);
+int spk_iota_i32(int32_t* v, int64_t n, spk_stream_t stream);
+int64_t spk_sort_workspace_bytes(int64_t n);
+/* stable LSD radix sort of (key,value) pairs on the low key_bits bits; result_in_tmp tells which buffers hold it */
+int spk_sort_pairs(int32_t* keys, int32_t* vals, int32_t* keys_tmp, int32_t* vals_tmp, int64_t n, int32_t key_bits,
+                   void* workspace, int32_t* result_in_tmp, spk_stream_t stream);
+int spk_segment_ptr(const int32_t* sorted_keys, int64_t n, int32_t n_seg, int32_t* ptr /*[n_seg+1]*/, spk_stream_t stream);
+int spk_gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* out, spk_stream_t stream);
+int spk_rel_incidence(const int32_t* t1, const int32_t* t2, int64_t e, int32_t n_rel, int32_t* keys, int32_t* vals,
+                      spk_stream_t stream);
+
+/* ---- K1/K5: dense products (replace a.mm(edge_h) layers.py:137, relation_embed.mm(W) models.py:77,
+ *      entity_embeddings.mm(W_entities) models.py:175 and their autograd) ---- */
+int spk_gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                int64_t M, int32_t N, int32_t K, int32_t accumulate, spk_stream_t stream);
+int64_t spk_gemm_tn_workspace_floats(int64_t M, int32_t Ka, int32_t Nb);
+/* C[Ka,Nb] (+)= A[M,Ka]^T * B[M,Nb], deterministic split over M */
+int spk_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                int64_t M, int32_t Ka, int32_t Nb, int32_t accumulate, float* workspace, spk_stream_t stream);
+
+/* ---- K2: fused attention forward (replaces SpGraphAttentionLayer.forward layers.py:124-175 for all
+ *      heads of a group, incl. both SpecialSpmmFinal calls, the divide and the ELU) ---- */
+typedef struct {
+    const int32_t* segptr; const int32_t* col; const int32_t* t1; const int32_t* t2;
+    const float* P1; int64_t ld1;
+    const float* P2; int64_t ld2;
+    const float* P3; int64_t ld3;
+    const float* mask; int64_t mask_stride;      /* [H][E] CSR-order dropout multipliers or null */
+    float* out; int64_t ldo;                     /* [n_rows, H*D] */
+    float* den; float* sw;                       /* [n_rows, H] */
+    int32_t* nanflag;                            /* sticky: set to 1 where the reference would assert (layers.py:147,167,172) */
+    int32_t n_rows; int32_t apply_elu; float alpha; int32_t reserved;
+    spk_geom geom;
+    spk_hub_tasks hub;
+} spk_edge_fwd_args;
+int spk_edge_attn_fwd(const spk_edge_fwd_args* args, spk_stream_t stream);
+
+/* ---- K3: backward over aggregation rows (autograd of layers.py:129-175, SpecialSpmmFunctionFinal.backward 67-79) ---- */
+typedef struct {
+    const int32_t* segptr; const int32_t* col; const int32_t* t1; const int32_t* t2;
+    const float* P1; int64_t ld1;
+    const float* P2; int64_t ld2;
+    const float* P3; int64_t ld3;
+    const float* mask; int64_t mask_stride;
+    const float* out; const float* dout; int64_t ldo;
+    const float* den;
+    float* G; int64_t ldg;                       /* [n_rows, ldg] dnum */
+    float* dP1; int64_t ldd1;                    /* [n_rows, width] */
+    float* rec;                                  /* [E, 2H] (w, ds) */
+    int32_t n_rows; int32_t apply_elu; float alpha; int32_t reserved;
+    spk_geom geom;
+    spk_hub_tasks hub;
+} spk_edge_bwd_rows_args;
+int spk_edge_attn_bwd_rows(const spk_edge_bwd_rows_args* args, spk_stream_t stream);
+
+/* ---- K4: backward segmented gather-sum, keyed on edge[1] (dP2~) or on relation id (dP3~) ---- */
+typedef struct {
+    const int32_t* segptr; const int32_t* src; const int32_t* pos;
+    const float* G; int64_t ldg;
+    const float* rec;
+    float* out; int64_t ldout;                   /* [n_seg, width] */
+    int32_t n_seg; int32_t reserved;
+    spk_geom geom;
+    spk_hub_tasks hub;
+} spk_seg_gather_args;
+int spk_edge_attn_bwd_segments(const spk_seg_gather_args* args, spk_stream_t stream);
+
+/* ---- stand-alone SpecialSpmmFunctionFinal (layers.py:51-79): out[i,:] = sum_{e in seg i} w[perm[e],:] ---- */
+int spk_spmm_rowsum_fwd(const int32_t* segptr, const int32_t* perm, const float* w, int64_t ldw, int32_t width,
+                        float* out, int64_t ldo, int32_t n_rows, spk_stream_t stream);
+int spk_spmm_rowsum_bwd(const int64_t* edge_row /*[E] original order*/, const float* gout, int64_t ldg, int32_t width,
+                        float* gw, int64_t ldw, int64_t n_edges, spk_stream_t stream);
+
+/* ---- K6: row-wise wrappers (models.py:160-161, 167-179) ---- */
+int spk_rownorm(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int32_t width, spk_stream_t stream);
+int spk_residual_norm_fwd(const float* ew, int64_t lde, const float* x2, int64_t ldx, const float* mask,
+                          float* out, int64_t ldo, float* inv_norm, int64_t n_rows, int32_t width, spk_stream_t stream);
+int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t ldo, const float* mask,
+                          const float* inv_norm, float* dew, int64_t lde, float* dx2, int64_t ldx,
+                          int64_t n_rows, int32_t width, spk_stream_t stream);
+int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPKBGAT_H */

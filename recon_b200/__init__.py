@@ -1,0 +1,14 @@
+"""recon_b200 -- B200-native (sm_100a) implementation of RECON's KBGAT sparse triple-attention hot path.
+
+Drop-in for the reference's `GAT/layers.py` + `GAT/models.py` module surface:
+    from recon_b200 import SpKBGATModified, SpGAT, SpGraphAttentionLayer, SpecialSpmmFunctionFinal, ConvKB
+All compute runs in libspkbgat.so (hand-written CUDA behind the C ABI of include/spkbgat.h);
+there is no CPU or PyTorch-eager fallback.
+"""
+from .graph import KGraph                                                   # noqa: F401
+from .layers import (SpecialSpmmFunctionFinal, SpecialSpmmFinal,           # noqa: F401
+                     SpGraphAttentionLayer, ConvKB)
+from .models import SpGAT, SpKBGATModified                                  # noqa: F401
+
+__all__ = ["KGraph", "SpecialSpmmFunctionFinal", "SpecialSpmmFinal", "SpGraphAttentionLayer", "ConvKB",
+           "SpGAT", "SpKBGATModified"]

@@ -1,0 +1,161 @@
+"""ctypes binding of libspkbgat.so (the C ABI declared in include/spkbgat.h).
+
+There is no CPU fallback: importing the ops without the built library, or calling them without a
+CUDA device, raises. The library is built in-tree by `__graft_entry__.build()` /
+`make -C recon_b200/csrc`.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f32p = C.POINTER(C.c_float)
+ABI_VERSION = 1
+
+
+class Geom(C.Structure):
+    _fields_ = [("n_heads", C.c_int32), ("d_head", C.c_int32), ("d_pad", C.c_int32), ("width", C.c_int32)]
+
+
+class HubTasks(C.Structure):
+    _fields_ = [("task_seg", C.c_void_p), ("task_beg", C.c_void_p), ("task_end", C.c_void_p),
+                ("hub_seg", C.c_void_p), ("hub_task_ptr", C.c_void_p),
+                ("partial", C.c_void_p), ("ldpart", C.c_int64),
+                ("n_tasks", C.c_int32), ("n_hubs", C.c_int32), ("hub_thresh", C.c_int32), ("reserved", C.c_int32)]
+
+
+class EdgeFwdArgs(C.Structure):
+    _fields_ = [("segptr", C.c_void_p), ("col", C.c_void_p), ("t1", C.c_void_p), ("t2", C.c_void_p),
+                ("P1", C.c_void_p), ("ld1", C.c_int64), ("P2", C.c_void_p), ("ld2", C.c_int64),
+                ("P3", C.c_void_p), ("ld3", C.c_int64),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int64),
+                ("out", C.c_void_p), ("ldo", C.c_int64), ("den", C.c_void_p), ("sw", C.c_void_p),
+                ("nanflag", C.c_void_p),
+                ("n_rows", C.c_int32), ("apply_elu", C.c_int32), ("alpha", C.c_float), ("reserved", C.c_int32),
+                ("geom", Geom), ("hub", HubTasks)]
+
+
+class EdgeBwdRowsArgs(C.Structure):
+    _fields_ = [("segptr", C.c_void_p), ("col", C.c_void_p), ("t1", C.c_void_p), ("t2", C.c_void_p),
+                ("P1", C.c_void_p), ("ld1", C.c_int64), ("P2", C.c_void_p), ("ld2", C.c_int64),
+                ("P3", C.c_void_p), ("ld3", C.c_int64),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int64),
+                ("out", C.c_void_p), ("dout", C.c_void_p), ("ldo", C.c_int64),
+                ("den", C.c_void_p),
+                ("G", C.c_void_p), ("ldg", C.c_int64), ("dP1", C.c_void_p), ("ldd1", C.c_int64),
+                ("rec", C.c_void_p),
+                ("n_rows", C.c_int32), ("apply_elu", C.c_int32), ("alpha", C.c_float), ("reserved", C.c_int32),
+                ("geom", Geom), ("hub", HubTasks)]
+
+
+class SegGatherArgs(C.Structure):
+    _fields_ = [("segptr", C.c_void_p), ("src", C.c_void_p), ("pos", C.c_void_p),
+                ("G", C.c_void_p), ("ldg", C.c_int64), ("rec", C.c_void_p),
+                ("out", C.c_void_p), ("ldout", C.c_int64),
+                ("n_seg", C.c_int32), ("reserved", C.c_int32),
+                ("geom", Geom), ("hub", HubTasks)]
+
+
+_VP, _I64, _I32 = C.c_void_p, C.c_int64, C.c_int32
+
+# name -> (restype, argtypes); every symbol include/spkbgat.h declares
+SIGNATURES = {
+    "spk_abi_version": (_I32, []),
+    "spk_last_error": (C.c_char_p, []),
+    "spk_launch_count": (_I64, []),
+    "spk_edges_concat": (_I32, [_VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I64, _I64, _VP, _VP]),
+    "spk_iota_i32": (_I32, [_VP, _I64, _VP]),
+    "spk_sort_workspace_bytes": (_I64, [_I64]),
+    "spk_sort_pairs": (_I32, [_VP, _VP, _VP, _VP, _I64, _I32, _VP, C.POINTER(_I32), _VP]),
+    "spk_segment_ptr": (_I32, [_VP, _I64, _I32, _VP, _VP]),
+    "spk_gather_i32": (_I32, [_VP, _VP, _I64, _VP, _VP]),
+    "spk_rel_incidence": (_I32, [_VP, _VP, _I64, _I32, _VP, _VP, _VP]),
+    "spk_gemm_nn": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
+    "spk_gemm_tn_workspace_floats": (_I64, [_I64, _I32, _I32]),
+    "spk_gemm_tn": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
+    "spk_edge_attn_fwd": (_I32, [C.POINTER(EdgeFwdArgs), _VP]),
+    "spk_edge_attn_bwd_rows": (_I32, [C.POINTER(EdgeBwdRowsArgs), _VP]),
+    "spk_edge_attn_bwd_segments": (_I32, [C.POINTER(SegGatherArgs), _VP]),
+    "spk_spmm_rowsum_fwd": (_I32, [_VP, _VP, _VP, _I64, _I32, _VP, _I64, _I32, _VP]),
+    "spk_spmm_rowsum_bwd": (_I32, [_VP, _VP, _I64, _I32, _VP, _I64, _I64, _VP]),
+    "spk_rownorm": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _VP]),
+    "spk_residual_norm_fwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
+    "spk_residual_norm_bwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP]),
+    "spk_mask_from_index": (_I32, [_VP, _I64, _VP, _I64, _VP]),
+}
+
+_lib = None
+current_tag = ""          # optional label appended to the next timed call's name (see profiler.py)
+
+
+class _Lib:
+    """Thin proxy over the CDLL: identical calls; when `timing` is a list every kernel-launching entry
+    point is bracketed by CUDA events on the launching stream (bench.py's per-kernel pass)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.timing = None
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if self.timing is None or SIGNATURES[name][1][-1:] != [_VP] or name.startswith("spk_gemm_tn_w"):
+            return fn
+
+        def timed(*args):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.timing.append((name[4:] + (":" + current_tag if current_tag else ""), e0, e1))
+            return rc
+        return timed
+
+
+def load():
+    """Load libspkbgat.so, bind every declared symbol, check the ABI version. Raises if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or make -C recon_b200/csrc). recon_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.spk_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libspkbgat ABI {lib.spk_abi_version()} != binding {ABI_VERSION}")
+    _lib = _Lib(lib)
+    return _lib
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("recon_b200 ops need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def launch_count():
+    """Kernels launched through libspkbgat so far (bench.py reports the delta as gpu_launches)."""
+    return int(load().spk_launch_count())
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().spk_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libspkbgat {what} failed (code {rc}): {msg}")

@@ -1,0 +1,225 @@
+// extern "C" surface of libspkbgat.so (declared in include/spkbgat.h): argument validation and
+// translation to the internal launchers. No device allocation, no retained pointers.
+#include "../../include/spkbgat.h"
+#include "spk_common.cuh"
+#include "spk_edge.cuh"
+#include "spk_gemm.cuh"
+#include "spk_graph.cuh"
+#include "spk_rowops.cuh"
+
+namespace spk {
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;      // kernels launched through this library (bench.py gpu_launches)
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED);
+    if (e == cudaSuccess) return 0;
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return 100 + (int)e;
+}
+
+static bool geom_ok(const spk_geom& g, LayerGeom* out, const char* who) {
+    if (g.n_heads < 1 || g.n_heads > SPK_MAX_HEADS || g.d_head < 1 || g.d_pad < g.d_head || (g.d_pad & 3) ||
+        (g.width & 7) || g.width < g.n_heads * g.d_pad + g.n_heads || g.width > 512) {
+        set_error("%s: bad geometry H=%d D=%d Dp=%d Wd=%d", who, g.n_heads, g.d_head, g.d_pad, g.width);
+        return false;
+    }
+    out->H = g.n_heads; out->D = g.d_head; out->Dp4 = g.d_pad / 4;
+    out->Dt4 = g.n_heads * g.d_pad / 4; out->Wd4 = g.width / 4;
+    return true;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static HubTasks hub_of(const spk_hub_tasks& h) {
+    HubTasks t;
+    t.task_seg = h.task_seg; t.task_beg = h.task_beg; t.task_end = h.task_end;
+    t.hub_seg = h.hub_seg; t.hub_task_ptr = h.hub_task_ptr;
+    t.partial = h.partial; t.ldpart = h.ldpart;
+    t.n_tasks = h.n_tasks; t.n_hubs = h.n_hubs;
+    t.hub_thresh = h.n_tasks > 0 ? h.hub_thresh : 0x7fffffff;
+    return t;
+}
+
+// ---- stand-alone SpecialSpmmFunctionFinal -------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spmm_rowsum_kernel(const int* __restrict__ segptr, const int* __restrict__ perm, const float* __restrict__ w, long ldw,
+                   int width, float* __restrict__ out, long ldo, int n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int beg = segptr[row], end = segptr[row + 1];
+    if (width == 1) {                                    // e_rowsum case (layers.py:150): lanes over edges
+        float s = 0.f;
+        for (int e = beg + lane; e < end; e += 32) s += w[(long)perm[e] * ldw];
+        s = warp_sum(s);
+        if (lane == 0) out[(long)row * ldo] = s;
+        return;
+    }
+    for (int c = lane; c < width; c += 32) {
+        float s = 0.f;
+        for (int e = beg; e < end; ++e) s += w[(long)perm[e] * ldw + c];
+        out[(long)row * ldo + c] = s;
+    }
+}
+
+__global__ void spmm_rowsum_bwd_kernel(const long long* __restrict__ edge_row, const float* __restrict__ g, long ldg,
+                                       int width, float* __restrict__ gw, long ldw, long n_edges) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_edges * width) return;
+    const long e = i / width; const int c = (int)(i % width);
+    gw[e * ldw + c] = g[(long)edge_row[e] * ldg + c];     // layers.py:75
+}
+
+}  // namespace spk
+
+using namespace spk;
+
+extern "C" {
+
+int spk_abi_version(void) { return SPK_ABI_VERSION; }
+const char* spk_last_error(void) { return g_err; }
+int64_t spk_launch_count(void) { return (int64_t)__atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int spk_edges_concat(const int64_t* edge, int64_t e1, const int64_t* edge_type, const int64_t* nhop, int64_t e2,
+                     int32_t* row, int32_t* col, int32_t* t1, int32_t* t2, int64_t n_nodes, int64_t n_rel,
+                     int32_t* err_flag, spk_stream_t stream) {
+    if (e1 + e2 >= (1LL << 31) || n_nodes >= (1LL << 31)) { set_error("edges_concat: sizes exceed int32"); return 1; }
+    if (e2 > 0 && !t2) { set_error("edges_concat: t2 required when 2-hop rows are given"); return 1; }
+    return edges_concat(reinterpret_cast<const long long*>(edge), e1, reinterpret_cast<const long long*>(edge_type),
+                        reinterpret_cast<const long long*>(nhop), e2, row, col, t1, t2, n_nodes, n_rel, err_flag,
+                        (cudaStream_t)stream);
+}
+int spk_iota_i32(int32_t* v, int64_t n, spk_stream_t stream) { return iota_i32(v, n, (cudaStream_t)stream); }
+int64_t spk_sort_workspace_bytes(int64_t n) { return radix_sort_workspace_bytes(n); }
+int spk_sort_pairs(int32_t* keys, int32_t* vals, int32_t* keys_tmp, int32_t* vals_tmp, int64_t n, int32_t key_bits,
+                   void* workspace, int32_t* result_in_tmp, spk_stream_t stream) {
+    if (key_bits < 1 || key_bits > 31) { set_error("sort_pairs: key_bits %d out of range", key_bits); return 1; }
+    return radix_sort_pairs(keys, vals, keys_tmp, vals_tmp, n, key_bits, workspace, result_in_tmp, (cudaStream_t)stream);
+}
+int spk_segment_ptr(const int32_t* sorted_keys, int64_t n, int32_t n_seg, int32_t* ptr, spk_stream_t stream) {
+    return segment_ptr(sorted_keys, n, n_seg, ptr, (cudaStream_t)stream);
+}
+int spk_gather_i32(const int32_t* src, const int32_t* idx, int64_t n, int32_t* out, spk_stream_t stream) {
+    return gather_i32(src, idx, n, out, (cudaStream_t)stream);
+}
+int spk_rel_incidence(const int32_t* t1, const int32_t* t2, int64_t e, int32_t n_rel, int32_t* keys, int32_t* vals,
+                      spk_stream_t stream) {
+    return rel_incidence(t1, t2, e, n_rel, keys, vals, (cudaStream_t)stream);
+}
+
+int spk_gemm_nn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                int64_t M, int32_t N, int32_t K, int32_t accumulate, spk_stream_t stream) {
+    if (lda < K || ldb < N || ldc < N) { set_error("gemm_nn: leading dimension too small"); return 1; }
+    return gemm_nn_simt(A, lda, B, ldb, C, ldc, M, N, K, accumulate, (cudaStream_t)stream);
+}
+int64_t spk_gemm_tn_workspace_floats(int64_t M, int32_t Ka, int32_t Nb) { return gemm_tn_workspace_floats(M, Ka, Nb); }
+int spk_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                int64_t M, int32_t Ka, int32_t Nb, int32_t accumulate, float* workspace, spk_stream_t stream) {
+    if (lda < Ka || ldb < Nb || ldc < Nb) { set_error("gemm_tn: leading dimension too small"); return 1; }
+    if (!workspace) { set_error("gemm_tn: workspace required"); return 1; }
+    return gemm_tn_simt(A, lda, B, ldb, C, ldc, M, Ka, Nb, accumulate, workspace, (cudaStream_t)stream);
+}
+
+int spk_edge_attn_fwd(const spk_edge_fwd_args* p, spk_stream_t stream) {
+    EdgeFwdArgs a;
+    if (!geom_ok(p->geom, &a.g, "edge_attn_fwd")) return 1;
+    if ((p->ld1 & 3) || (p->ld2 & 3) || (p->ld3 & 3) || p->ld1 < p->geom.width || p->ld2 < p->geom.width ||
+        p->ld3 < p->geom.width || !aligned16(p->P1) || !aligned16(p->P2) || !aligned16(p->P3)) {
+        set_error("edge_attn_fwd: projected tables must be 16-byte aligned with ld >= width, ld %% 4 == 0");
+        return 1;
+    }
+    a.segptr = p->segptr; a.col = p->col; a.t1 = p->t1; a.t2 = p->t2;
+    a.P1 = p->P1; a.ld1 = p->ld1; a.P2 = p->P2; a.ld2 = p->ld2; a.P3 = p->P3; a.ld3 = p->ld3;
+    a.mask = p->mask; a.mask_stride = p->mask_stride;
+    a.out = p->out; a.ldo = p->ldo; a.den = p->den; a.sw = p->sw; a.nanflag = p->nanflag;
+    a.n_rows = p->n_rows; a.alpha = p->alpha; a.apply_elu = p->apply_elu;
+    a.out_vec = (p->geom.d_head % 4 == 0) && (p->ldo % 4 == 0) && aligned16(p->out);
+    a.hub = hub_of(p->hub);
+    if (a.hub.n_tasks > 0 && (a.hub.ldpart < p->geom.width + 2 * SPK_MAX_HEADS || (a.hub.ldpart & 3) || !aligned16(a.hub.partial))) {
+        set_error("edge_attn_fwd: hub partial buffer needs ldpart >= width+8, ldpart %% 4 == 0");
+        return 1;
+    }
+    return launch_edge_fwd(a, (cudaStream_t)stream);
+}
+
+int spk_edge_attn_bwd_rows(const spk_edge_bwd_rows_args* p, spk_stream_t stream) {
+    EdgeBwdRowsArgs a;
+    if (!geom_ok(p->geom, &a.g, "edge_attn_bwd_rows")) return 1;
+    if ((p->ld1 & 3) || (p->ld2 & 3) || (p->ld3 & 3) || (p->ldg & 3) || (p->ldd1 & 3) || p->ldg < p->geom.n_heads * p->geom.d_pad ||
+        p->ldd1 < p->geom.width || !aligned16(p->P1) || !aligned16(p->P2) || !aligned16(p->P3) || !aligned16(p->G) ||
+        !aligned16(p->dP1) || (reinterpret_cast<uintptr_t>(p->rec) & 7)) {
+        set_error("edge_attn_bwd_rows: bad leading dimension or alignment");
+        return 1;
+    }
+    a.segptr = p->segptr; a.col = p->col; a.t1 = p->t1; a.t2 = p->t2;
+    a.P1 = p->P1; a.ld1 = p->ld1; a.P2 = p->P2; a.ld2 = p->ld2; a.P3 = p->P3; a.ld3 = p->ld3;
+    a.mask = p->mask; a.mask_stride = p->mask_stride;
+    a.out = p->out; a.dout = p->dout; a.ldo = p->ldo; a.den = p->den;
+    a.G = p->G; a.ldg = p->ldg; a.dP1 = p->dP1; a.ldd1 = p->ldd1; a.rec = p->rec;
+    a.n_rows = p->n_rows; a.alpha = p->alpha; a.apply_elu = p->apply_elu;
+    a.out_vec = (p->geom.d_head % 4 == 0) && (p->ldo % 4 == 0) && aligned16(p->out) && aligned16(p->dout);
+    a.hub = hub_of(p->hub);
+    if (a.hub.n_tasks > 0 && a.hub.ldpart < 2 * SPK_MAX_HEADS) { set_error("edge_attn_bwd_rows: hub ldpart must be >= 8"); return 1; }
+    return launch_edge_bwd_rows(a, (cudaStream_t)stream);
+}
+
+int spk_edge_attn_bwd_segments(const spk_seg_gather_args* p, spk_stream_t stream) {
+    SegGatherArgs a;
+    if (!geom_ok(p->geom, &a.g, "edge_attn_bwd_segments")) return 1;
+    if ((p->ldg & 3) || (p->ldout & 3) || p->ldout < p->geom.width || p->ldg < p->geom.n_heads * p->geom.d_pad ||
+        !aligned16(p->G) || !aligned16(p->out) || (reinterpret_cast<uintptr_t>(p->rec) & 7)) {
+        set_error("edge_attn_bwd_segments: bad leading dimension or alignment");
+        return 1;
+    }
+    a.segptr = p->segptr; a.src = p->src; a.pos = p->pos; a.G = p->G; a.ldg = p->ldg; a.rec = p->rec;
+    a.outp = p->out; a.ldout = p->ldout; a.n_seg = p->n_seg;
+    a.hub = hub_of(p->hub);
+    if (a.hub.n_tasks > 0 && (a.hub.ldpart < p->geom.width || (a.hub.ldpart & 3) || !aligned16(a.hub.partial))) {
+        set_error("edge_attn_bwd_segments: hub partial buffer needs ldpart >= width");
+        return 1;
+    }
+    return launch_seg_gather(a, (cudaStream_t)stream);
+}
+
+int spk_spmm_rowsum_fwd(const int32_t* segptr, const int32_t* perm, const float* w, int64_t ldw, int32_t width,
+                        float* out, int64_t ldo, int32_t n_rows, spk_stream_t stream) {
+    if (n_rows <= 0) return 0;
+    spmm_rowsum_kernel<<<(n_rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(segptr, perm, w, ldw, width, out, ldo, n_rows);
+    return check_launch("spmm_rowsum");
+}
+int spk_spmm_rowsum_bwd(const int64_t* edge_row, const float* gout, int64_t ldg, int32_t width, float* gw, int64_t ldw,
+                        int64_t n_edges, spk_stream_t stream) {
+    const long total = n_edges * width;
+    if (total <= 0) return 0;
+    spmm_rowsum_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const long long*>(edge_row), gout, ldg, width, gw, ldw, n_edges);
+    return check_launch("spmm_rowsum_bwd");
+}
+
+int spk_rownorm(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t n_rows, int32_t width, spk_stream_t stream) {
+    return rownorm(x, ldx, y, ldy, n_rows, width, (cudaStream_t)stream);
+}
+int spk_residual_norm_fwd(const float* ew, int64_t lde, const float* x2, int64_t ldx, const float* mask, float* out,
+                          int64_t ldo, float* inv_norm, int64_t n_rows, int32_t width, spk_stream_t stream) {
+    return residual_norm(ew, lde, x2, ldx, mask, out, ldo, inv_norm, n_rows, width, (cudaStream_t)stream);
+}
+int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t ldo, const float* mask,
+                          const float* inv_norm, float* dew, int64_t lde, float* dx2, int64_t ldx, int64_t n_rows,
+                          int32_t width, spk_stream_t stream) {
+    return residual_norm_bwd(g, ldg, out, ldo, mask, inv_norm, dew, lde, dx2, ldx, n_rows, width, (cudaStream_t)stream);
+}
+int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream) {
+    return mask_from_index(reinterpret_cast<const long long*>(idx), n_idx, mask, n_rows, (cudaStream_t)stream);
+}
+
+}  // extern "C"

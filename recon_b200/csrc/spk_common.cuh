@@ -1,0 +1,61 @@
+// Shared device/host helpers for libspkbgat (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#define SPK_MAX_HEADS 4          // heads fused per edge-kernel launch (q columns live in one float4)
+#define SPK_WARPS_PER_CTA 8
+#define SPK_CTA_THREADS (SPK_WARPS_PER_CTA * 32)
+
+namespace spk {
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // returns 0 or error code after a kernel launch
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+// streaming (read-once) 128-bit load: do not allocate in L1
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+    return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ void f4fma(float4& acc, float w, float4 v) {
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+}
+__device__ __forceinline__ float f4dot(float4 a, float4 b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float f4get(const float4& v, int k) {
+    return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+__device__ __forceinline__ float sel4(int h, float a, float b, float c, float d) {
+    return h == 0 ? a : (h == 1 ? b : (h == 2 ? c : d));
+}
+
+// Geometry of one fused attention-layer group. Rows of the projected tables are
+//   [ H*Dp floats of projection | H score scalars q | zero pad ]  (width Wd, multiple of 8)
+// Dp = D rounded up to 4 so a head never straddles a float4 chunk.
+struct LayerGeom {
+    int H;        // heads in this launch (<= SPK_MAX_HEADS)
+    int D;        // out_features per head
+    int Dp4;      // Dp / 4
+    int Dt4;      // H * Dp / 4 : number of projection chunks; chunk Dt4 holds the q scalars
+    int Wd4;      // Wd / 4 : chunks per table row
+};
+
+}  // namespace spk

@@ -1,0 +1,460 @@
+// K3 / K4: backward of the fused attention-layer group (closed form of SURVEY.md 8 a-5; the
+// reference gets it from autograd over GAT/layers.py:124-175 + SpecialSpmmFunctionFinal.backward
+// layers.py:67-79).
+//
+// K3 (rows, CSR order; one warp per aggregation row i):
+//   dh = dOut * ELU'(h),  dnum = dh/den,  dden = -(dh.h)/den
+//   per edge: t = dnum . m_e,  w = msk*ee,  ds = -(msk*t + dden) * ee * LeakyReLU'(s)
+//   emits rec[e] = (w, ds) per head, G[i] = dnum, dP1~[i] = [ (sum w) * dnum | sum ds | 0 ]
+// K4 (segments keyed on edge[1] = CSC, or on relation id): out[seg] = [ sum w*G[row_e] | sum ds | 0 ]
+//   which is dP2~ (per gathered node) resp. dP3~ (per relation).
+// Both are deterministic: fixed edge order inside a segment, hub segments split into chunks whose
+// partials are added in chunk order.
+#include "spk_edge.cuh"
+
+namespace spk {
+
+// ---- loads of the unpadded [n_rows, H*D] activations into padded float4 chunks ----------------
+__device__ __forceinline__ float4 load_act_chunk(const float* base, int h, int off, int D, int vec) {
+    const float* p = base + (long)h * D + off;
+    if (vec) return ldg4(p);
+    float4 r;
+    r.x = off + 0 < D ? __ldg(p + 0) : 0.f;
+    r.y = off + 1 < D ? __ldg(p + 1) : 0.f;
+    r.z = off + 2 < D ? __ldg(p + 2) : 0.f;
+    r.w = off + 3 < D ? __ldg(p + 3) : 0.f;
+    return r;
+}
+
+template <int NCH>
+struct RowCtx {
+    float4 dnum[NCH];
+    int hc[NCH];
+    float q1[SPK_MAX_HEADS];
+    float dden[SPK_MAX_HEADS];
+    float c1[SPK_MAX_HEADS];       // dnum . P1[i] per head
+};
+
+template <int NCH>
+__device__ __forceinline__ void bwd_row_prologue(const EdgeBwdRowsArgs& a, int row, int lane, RowCtx<NCH>& rc) {
+    const LayerGeom g = a.g;
+    float pdh[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+    float pc1[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+    float den[SPK_MAX_HEADS];
+#pragma unroll
+    for (int h = 0; h < SPK_MAX_HEADS; ++h) den[h] = h < g.H ? __ldg(a.den + (long)row * g.H + h) : 1.f;
+    const float4 q1v = ldg4(a.P1 + (long)row * a.ld1 + (long)g.Dt4 * 4);
+    rc.q1[0] = q1v.x; rc.q1[1] = q1v.y; rc.q1[2] = q1v.z; rc.q1[3] = q1v.w;
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+        const int c4 = lane + 32 * ci;
+        rc.hc[ci] = 0;
+        rc.dnum[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 >= g.Dt4) continue;
+        const int h = c4 / g.Dp4;
+        rc.hc[ci] = h;
+        const int off = (c4 - h * g.Dp4) * 4;
+        const float4 o4 = load_act_chunk(a.out + (long)row * a.ldo, h, off, g.D, a.out_vec);
+        const float4 g4 = load_act_chunk(a.dout + (long)row * a.ldo, h, off, g.D, a.out_vec);
+        const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+        const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+        float dh[4], hv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (a.apply_elu) {
+                // out = ELU(h): h>0 -> out=h, d=1 ; else out=e^h-1, d=out+1, h=log1p(out)
+                const bool pos = o[k] > 0.f;
+                dh[k] = pos ? gg[k] : gg[k] * (o[k] + 1.f);
+                hv[k] = pos ? o[k] : (o[k] > -1.f ? log1pf(o[k]) : 0.f);
+            } else {
+                dh[k] = gg[k];
+                hv[k] = o[k];
+            }
+        }
+        const float d = sel4(h, den[0], den[1], den[2], den[3]);
+        const float dot_h = fmaf(dh[0], hv[0], fmaf(dh[1], hv[1], fmaf(dh[2], hv[2], dh[3] * hv[3])));
+        rc.dnum[ci] = make_float4(dh[0] / d, dh[1] / d, dh[2] / d, dh[3] / d);
+        const float4 p1 = ldg4(a.P1 + (long)row * a.ld1 + c4 * 4);
+        const float dot_c = f4dot(rc.dnum[ci], p1);
+#pragma unroll
+        for (int hh = 0; hh < SPK_MAX_HEADS; ++hh) {
+            pdh[hh] += (h == hh) ? dot_h : 0.f;
+            pc1[hh] += (h == hh) ? dot_c : 0.f;
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < SPK_MAX_HEADS; ++h) {
+        rc.dden[h] = 0.f; rc.c1[h] = 0.f;
+        if (h < g.H) {
+            rc.dden[h] = -warp_sum(pdh[h]) / den[h];
+            rc.c1[h] = warp_sum(pc1[h]);
+        }
+    }
+}
+
+template <int NCH, bool HAS2>
+__device__ __forceinline__ void bwd_row_edges(const EdgeBwdRowsArgs& a, int beg, int end, int lane,
+                                              const RowCtx<NCH>& rc, float (&usum)[SPK_MAX_HEADS],
+                                              float (&swsum)[SPK_MAX_HEADS]) {
+    constexpr int U = (NCH <= 2) ? 4 : 2;
+    const LayerGeom g = a.g;
+    const int qlane = g.Dt4 & 31, qci = g.Dt4 >> 5;
+    const bool has_mask = a.mask != nullptr;
+    for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        int my_col = 0, my_t1 = 0, my_t2 = -1;
+        float my_m[SPK_MAX_HEADS] = {1.f, 1.f, 1.f, 1.f};
+        float my_w[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, my_ds[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+        if (lane < n) {
+            my_col = __ldg(a.col + base + lane);
+            my_t1 = __ldg(a.t1 + base + lane);
+            if (HAS2) my_t2 = __ldg(a.t2 + base + lane);
+            if (has_mask) {
+#pragma unroll
+                for (int h = 0; h < SPK_MAX_HEADS; ++h)
+                    if (h < g.H) my_m[h] = __ldg(a.mask + (long)h * a.mask_stride + base + lane);
+            }
+        }
+        for (int u0 = 0; u0 < n; u0 += U) {
+            float4 v[U][NCH];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = u0 + u;
+                const int j = __shfl_sync(0xffffffffu, my_col, idx & 31);
+                const int k1 = __shfl_sync(0xffffffffu, my_t1, idx & 31);
+                int k2 = -1;
+                if (HAS2) k2 = __shfl_sync(0xffffffffu, my_t2, idx & 31);
+                const float* p2 = a.P2 + (long)j * a.ld2;
+                const float* p3 = a.P3 + (long)k1 * a.ld3;
+                const float* p3b = a.P3 + (long)(k2 < 0 ? 0 : k2) * a.ld3;
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int c4 = lane + 32 * ci;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx < n && c4 < g.Wd4) {
+                        x = f4add(ldg4(p2 + c4 * 4), ldg4(p3 + c4 * 4));
+                        if (HAS2 && k2 >= 0) x = f4add(x, ldg4(p3b + c4 * 4));
+                    }
+                    v[u][ci] = x;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = u0 + u;
+                if (idx >= n) break;
+                float4 qv = v[u][0];
+#pragma unroll
+                for (int ci = 1; ci < NCH; ++ci)
+                    if (qci == ci) qv = v[u][ci];
+                float pd[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const float d = f4dot(rc.dnum[ci], v[u][ci]);     // dnum is 0 on q / pad chunks
+#pragma unroll
+                    for (int h = 0; h < SPK_MAX_HEADS; ++h) pd[h] += (rc.hc[ci] == h) ? d : 0.f;
+                }
+#pragma unroll
+                for (int h = 0; h < SPK_MAX_HEADS; ++h) {
+                    if (h < g.H) {
+                        const float t = rc.c1[h] + warp_sum(pd[h]);
+                        const float s = rc.q1[h] + __shfl_sync(0xffffffffu, f4get(qv, h), qlane);
+                        const float slope = s > 0.f ? 1.f : a.alpha;
+                        const float ee = expf(-(s * slope));
+                        float m = 1.f;
+                        if (has_mask) m = __shfl_sync(0xffffffffu, my_m[h], idx & 31);
+                        const float w = ee * m;
+                        const float ds = -(m * t + rc.dden[h]) * ee * slope;
+                        usum[h] += ds;
+                        swsum[h] += w;
+                        if (lane == idx) { my_w[h] = w; my_ds[h] = ds; }
+                    }
+                }
+            }
+        }
+        if (lane < n) {
+            float* r = a.rec + (long)(base + lane) * (2 * g.H);
+#pragma unroll
+            for (int h = 0; h < SPK_MAX_HEADS; ++h)
+                if (h < g.H) *reinterpret_cast<float2*>(r + 2 * h) = make_float2(my_w[h], my_ds[h]);
+        }
+    }
+}
+
+template <int NCH>
+__device__ __forceinline__ void bwd_row_store(const EdgeBwdRowsArgs& a, int row, int lane, const RowCtx<NCH>& rc,
+                                              const float (&usum)[SPK_MAX_HEADS], const float (&swsum)[SPK_MAX_HEADS],
+                                              bool store_g, bool store_dp1) {
+    const LayerGeom g = a.g;
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+        const int c4 = lane + 32 * ci;
+        if (store_g && c4 * 4 < a.ldg)
+            *reinterpret_cast<float4*>(a.G + (long)row * a.ldg + c4 * 4) = rc.dnum[ci];
+        if (store_dp1 && c4 < g.Wd4) {
+            float4 o;
+            if (c4 < g.Dt4) {
+                const float s = sel4(rc.hc[ci], swsum[0], swsum[1], swsum[2], swsum[3]);
+                o = make_float4(s * rc.dnum[ci].x, s * rc.dnum[ci].y, s * rc.dnum[ci].z, s * rc.dnum[ci].w);
+            } else if (c4 == g.Dt4) {
+                o = make_float4(usum[0], usum[1], usum[2], usum[3]);
+            } else {
+                o = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *reinterpret_cast<float4*>(a.dP1 + (long)row * a.ldd1 + c4 * 4) = o;
+        }
+    }
+}
+
+template <int NCH, bool HAS2>
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+edge_bwd_rows_kernel(const EdgeBwdRowsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= a.n_rows) return;
+    const int beg = __ldg(a.segptr + row), end = __ldg(a.segptr + row + 1);
+    if (end - beg > a.hub.hub_thresh) return;
+    RowCtx<NCH> rc;
+    bwd_row_prologue<NCH>(a, row, lane, rc);
+    float usum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, swsum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+    bwd_row_edges<NCH, HAS2>(a, beg, end, lane, rc, usum, swsum);
+    bwd_row_store<NCH>(a, row, lane, rc, usum, swsum, true, true);
+}
+
+template <int NCH, bool HAS2>
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+edge_bwd_rows_tasks_kernel(const EdgeBwdRowsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (task >= a.hub.n_tasks) return;
+    const int row = __ldg(a.hub.task_seg + task);
+    RowCtx<NCH> rc;
+    bwd_row_prologue<NCH>(a, row, lane, rc);
+    float usum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, swsum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+    bwd_row_edges<NCH, HAS2>(a, __ldg(a.hub.task_beg + task), __ldg(a.hub.task_end + task), lane, rc, usum, swsum);
+    if (lane < SPK_MAX_HEADS) {
+        float* part = a.hub.partial + (long)task * a.hub.ldpart;
+        part[lane] = sel4(lane, usum[0], usum[1], usum[2], usum[3]);
+        part[SPK_MAX_HEADS + lane] = sel4(lane, swsum[0], swsum[1], swsum[2], swsum[3]);
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+edge_bwd_rows_hub_finalize_kernel(const EdgeBwdRowsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int hub = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (hub >= a.hub.n_hubs) return;
+    const int row = __ldg(a.hub.hub_seg + hub);
+    RowCtx<NCH> rc;
+    bwd_row_prologue<NCH>(a, row, lane, rc);
+    float usum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, swsum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+    const int t0 = __ldg(a.hub.hub_task_ptr + hub), t1 = __ldg(a.hub.hub_task_ptr + hub + 1);
+    for (int t = t0; t < t1; ++t) {
+        const float* part = a.hub.partial + (long)t * a.hub.ldpart;
+#pragma unroll
+        for (int h = 0; h < SPK_MAX_HEADS; ++h) { usum[h] += part[h]; swsum[h] += part[SPK_MAX_HEADS + h]; }
+    }
+    bwd_row_store<NCH>(a, row, lane, rc, usum, swsum, true, true);
+}
+
+template <int NCH, bool HAS2>
+static int launch_bwd_rows_t(const EdgeBwdRowsArgs& a, cudaStream_t s) {
+    if (a.n_rows > 0) {
+        const unsigned grid = (a.n_rows + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+        edge_bwd_rows_kernel<NCH, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (int rc = check_launch("edge_bwd_rows")) return rc;
+    }
+    if (a.hub.n_tasks > 0) {
+        const unsigned grid = (a.hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+        edge_bwd_rows_tasks_kernel<NCH, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (int rc = check_launch("edge_bwd_rows_tasks")) return rc;
+        const unsigned gridh = (a.hub.n_hubs + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+        edge_bwd_rows_hub_finalize_kernel<NCH><<<gridh, SPK_CTA_THREADS, 0, s>>>(a);
+        if (int rc = check_launch("edge_bwd_rows_hub_finalize")) return rc;
+    }
+    return 0;
+}
+
+int launch_edge_bwd_rows(const EdgeBwdRowsArgs& a, cudaStream_t s) {
+    const int nch = (a.g.Wd4 + 31) / 32;
+    const bool has2 = a.t2 != nullptr;
+#define SPK_CASE(N) case N: return has2 ? launch_bwd_rows_t<N, true>(a, s) : launch_bwd_rows_t<N, false>(a, s);
+    switch (nch) {
+        SPK_CASE(1) SPK_CASE(2) SPK_CASE(3) SPK_CASE(4)
+        default: set_error("edge_bwd_rows: row width %d floats exceeds the supported 512", a.g.Wd4 * 4); return 2;
+    }
+#undef SPK_CASE
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: out[seg] = [ sum_e w_e,h * G[src_e] | sum_e ds_e,h | 0 ]
+// ------------------------------------------------------------------------------------------------
+template <int NCH>
+struct SegAcc {
+    float4 acc[NCH];
+    float vs[SPK_MAX_HEADS];     // lane-local partial sums of ds (reduced across the warp at the end)
+};
+
+template <int NCH>
+__device__ __forceinline__ void seg_accumulate(const SegGatherArgs& a, int beg, int end, int lane,
+                                               const int (&hc)[NCH], SegAcc<NCH>& st) {
+    constexpr int U = (NCH <= 2) ? 4 : 2;
+    const LayerGeom g = a.g;
+    for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        int my_src = 0;
+        float my_w[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+        if (lane < n) {
+            my_src = __ldg(a.src + base + lane);
+            const int p = __ldg(a.pos + base + lane);
+            const float* r = a.rec + (long)p * (2 * g.H);
+#pragma unroll
+            for (int h = 0; h < SPK_MAX_HEADS; ++h) {
+                if (h < g.H) {
+                    const float2 wd = __ldg(reinterpret_cast<const float2*>(r + 2 * h));
+                    my_w[h] = wd.x;
+                    st.vs[h] += wd.y;
+                }
+            }
+        }
+        for (int u0 = 0; u0 < n; u0 += U) {
+            float4 v[U][NCH];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = u0 + u;
+                const int i = __shfl_sync(0xffffffffu, my_src, idx & 31);
+                const float* gp = a.G + (long)i * a.ldg;
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci) {
+                    const int c4 = lane + 32 * ci;
+                    v[u][ci] = (idx < n && c4 < g.Dt4) ? ldg4(gp + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int idx = u0 + u;
+                if (idx >= n) break;
+                float w[SPK_MAX_HEADS];
+#pragma unroll
+                for (int h = 0; h < SPK_MAX_HEADS; ++h)
+                    w[h] = h < g.H ? __shfl_sync(0xffffffffu, my_w[h], idx & 31) : 0.f;
+#pragma unroll
+                for (int ci = 0; ci < NCH; ++ci)
+                    f4fma(st.acc[ci], sel4(hc[ci], w[0], w[1], w[2], w[3]), v[u][ci]);
+            }
+        }
+    }
+}
+
+template <int NCH>
+__device__ __forceinline__ void seg_init(const LayerGeom& g, int lane, int (&hc)[NCH], SegAcc<NCH>& st) {
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+        const int c4 = lane + 32 * ci;
+        hc[ci] = c4 < g.Dt4 ? c4 / g.Dp4 : 0;
+        st.acc[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] = 0.f;
+}
+
+// vs must already be warp-reduced (identical in all lanes)
+template <int NCH>
+__device__ __forceinline__ void seg_store(float* dst, const LayerGeom& g, int lane, const SegAcc<NCH>& st) {
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+        const int c4 = lane + 32 * ci;
+        if (c4 >= g.Wd4) continue;
+        float4 o = st.acc[ci];
+        if (c4 == g.Dt4) o = make_float4(st.vs[0], st.vs[1], st.vs[2], st.vs[3]);
+        else if (c4 > g.Dt4) o = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(dst + c4 * 4) = o;
+    }
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+seg_gather_kernel(const SegGatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int seg = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (seg >= a.n_seg) return;
+    const int beg = __ldg(a.segptr + seg), end = __ldg(a.segptr + seg + 1);
+    if (end - beg > a.hub.hub_thresh) return;
+    int hc[NCH];
+    SegAcc<NCH> st;
+    seg_init<NCH>(a.g, lane, hc, st);
+    seg_accumulate<NCH>(a, beg, end, lane, hc, st);
+#pragma unroll
+    for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] = warp_sum(st.vs[h]);
+    seg_store<NCH>(a.outp + (long)seg * a.ldout, a.g, lane, st);
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+seg_gather_tasks_kernel(const SegGatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (task >= a.hub.n_tasks) return;
+    int hc[NCH];
+    SegAcc<NCH> st;
+    seg_init<NCH>(a.g, lane, hc, st);
+    seg_accumulate<NCH>(a, __ldg(a.hub.task_beg + task), __ldg(a.hub.task_end + task), lane, hc, st);
+#pragma unroll
+    for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] = warp_sum(st.vs[h]);
+    seg_store<NCH>(a.hub.partial + (long)task * a.hub.ldpart, a.g, lane, st);
+}
+
+template <int NCH>
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+seg_gather_hub_finalize_kernel(const SegGatherArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int hub = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (hub >= a.hub.n_hubs) return;
+    const int seg = __ldg(a.hub.hub_seg + hub);
+    int hc[NCH];
+    SegAcc<NCH> st;
+    seg_init<NCH>(a.g, lane, hc, st);
+    const int t0 = __ldg(a.hub.hub_task_ptr + hub), t1 = __ldg(a.hub.hub_task_ptr + hub + 1);
+    for (int t = t0; t < t1; ++t) {
+        const float* part = a.hub.partial + (long)t * a.hub.ldpart;
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+            const int c4 = lane + 32 * ci;
+            if (c4 < a.g.Dt4) st.acc[ci] = f4add(st.acc[ci], *reinterpret_cast<const float4*>(part + c4 * 4));
+        }
+#pragma unroll
+        for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] += part[a.g.Dt4 * 4 + h];
+    }
+    seg_store<NCH>(a.outp + (long)seg * a.ldout, a.g, lane, st);
+}
+
+template <int NCH>
+static int launch_seg_t(const SegGatherArgs& a, cudaStream_t s) {
+    if (a.n_seg > 0) {
+        const unsigned grid = (a.n_seg + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+        seg_gather_kernel<NCH><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (int rc = check_launch("seg_gather")) return rc;
+    }
+    if (a.hub.n_tasks > 0) {
+        const unsigned grid = (a.hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+        seg_gather_tasks_kernel<NCH><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (int rc = check_launch("seg_gather_tasks")) return rc;
+        const unsigned gridh = (a.hub.n_hubs + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+        seg_gather_hub_finalize_kernel<NCH><<<gridh, SPK_CTA_THREADS, 0, s>>>(a);
+        if (int rc = check_launch("seg_gather_hub_finalize")) return rc;
+    }
+    return 0;
+}
+
+int launch_seg_gather(const SegGatherArgs& a, cudaStream_t s) {
+    const int nch = (a.g.Wd4 + 31) / 32;
+    switch (nch) {
+        case 1: return launch_seg_t<1>(a, s);
+        case 2: return launch_seg_t<2>(a, s);
+        case 3: return launch_seg_t<3>(a, s);
+        case 4: return launch_seg_t<4>(a, s);
+        default: set_error("seg_gather: row width %d floats exceeds the supported 512", a.g.Wd4 * 4); return 2;
+    }
+}
+
+}  // namespace spk

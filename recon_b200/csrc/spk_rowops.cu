@@ -1,0 +1,100 @@
+// K6: row-wise wrappers around the attention layers (GAT/models.py:160-161,167-179):
+//   rownorm        : y = x / max(||x||_2, 1e-12)                         (F.normalize, in place allowed)
+//   residual_norm  : v = EW + mask*x2 ; out = v / max(||v||, 1e-12)      (models.py:175-179), saves 1/||v||
+//   residual_norm_bwd : dv = (g - out*(out.g)) / ||v|| ; dEW = dv ; dx2 = mask*dv
+//   mask_from_index: mask[idx[b]] = 1                                    (models.py:167-173)
+// One warp per row, float4 when the row allows it; HBM-bound streaming.
+#include "spk_common.cuh"
+#include "spk_rowops.cuh"
+
+namespace spk {
+namespace {
+
+__global__ void __launch_bounds__(256)
+rownorm_kernel(const float* __restrict__ x, long ldx, float* __restrict__ y, long ldy, long n_rows, int width) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* xr = x + row * ldx;
+    float ss = 0.f;
+    for (int c = lane; c < width; c += 32) { const float v = xr[c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float* yr = y + row * ldy;
+    for (int c = lane; c < width; c += 32) yr[c] = xr[c] * inv;
+}
+
+__global__ void __launch_bounds__(256)
+residual_norm_kernel(const float* __restrict__ ew, long lde, const float* __restrict__ x2, long ldx,
+                     const float* __restrict__ mask, float* __restrict__ out, long ldo,
+                     float* __restrict__ inv_norm, long n_rows, int width) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float m = mask[row];
+    const float* e = ew + row * lde;
+    const float* x = x2 + row * ldx;
+    float ss = 0.f;
+    for (int c = lane; c < width; c += 32) { const float v = e[c] + m * x[c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    float* o = out + row * ldo;
+    for (int c = lane; c < width; c += 32) o[c] = (e[c] + m * x[c]) * inv;
+    if (lane == 0) inv_norm[row] = inv;
+}
+
+__global__ void __launch_bounds__(256)
+residual_norm_bwd_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ out, long ldo,
+                         const float* __restrict__ mask, const float* __restrict__ inv_norm,
+                         float* __restrict__ dew, long lde, float* __restrict__ dx2, long ldx,
+                         long n_rows, int width) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float* gr = g + row * ldg;
+    const float* o = out + row * ldo;
+    float dot = 0.f;
+    for (int c = lane; c < width; c += 32) dot = fmaf(gr[c], o[c], dot);
+    dot = warp_sum(dot);
+    const float inv = inv_norm[row];
+    const float m = mask[row];
+    // ||v|| < eps -> F.normalize divides by the constant eps: dv = g / eps
+    const bool clamped = inv >= 1e12f;
+    for (int c = lane; c < width; c += 32) {
+        const float dv = clamped ? gr[c] * inv : (gr[c] - o[c] * dot) * inv;
+        dew[row * lde + c] = dv;
+        dx2[row * ldx + c] = m * dv;
+    }
+}
+
+__global__ void mask_from_index_kernel(const long long* __restrict__ idx, long n_idx, float* __restrict__ mask, long n_rows) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_idx) return;
+    const long long r = idx[i];
+    if (r >= 0 && r < n_rows) mask[r] = 1.0f;        // idempotent store: duplicates are harmless
+}
+}  // namespace
+
+int rownorm(const float* x, long ldx, float* y, long ldy, long n_rows, int width, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    rownorm_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(x, ldx, y, ldy, n_rows, width);
+    return check_launch("rownorm");
+}
+int residual_norm(const float* ew, long lde, const float* x2, long ldx, const float* mask, float* out, long ldo,
+                  float* inv_norm, long n_rows, int width, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    residual_norm_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(ew, lde, x2, ldx, mask, out, ldo, inv_norm, n_rows, width);
+    return check_launch("residual_norm");
+}
+int residual_norm_bwd(const float* g, long ldg, const float* out, long ldo, const float* mask, const float* inv_norm,
+                      float* dew, long lde, float* dx2, long ldx, long n_rows, int width, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    residual_norm_bwd_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(g, ldg, out, ldo, mask, inv_norm, dew, lde, dx2, ldx, n_rows, width);
+    return check_launch("residual_norm_bwd");
+}
+int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, cudaStream_t s) {
+    if (n_idx <= 0) return 0;
+    mask_from_index_kernel<<<(unsigned)((n_idx + 255) / 256), 256, 0, s>>>(idx, n_idx, mask, n_rows);
+    return check_launch("mask_from_index");
+}
+}  // namespace spk

@@ -1,0 +1,10 @@
+#pragma once
+#include <cuda_runtime.h>
+namespace spk {
+int rownorm(const float* x, long ldx, float* y, long ldy, long n_rows, int width, cudaStream_t s);
+int residual_norm(const float* ew, long lde, const float* x2, long ldx, const float* mask, float* out, long ldo,
+                  float* inv_norm, long n_rows, int width, cudaStream_t s);
+int residual_norm_bwd(const float* g, long ldg, const float* out, long ldo, const float* mask, const float* inv_norm,
+                      float* dew, long lde, float* dx2, long ldx, long n_rows, int width, cudaStream_t s);
+int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, cudaStream_t s);
+}  // namespace spk

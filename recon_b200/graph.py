@@ -1,0 +1,178 @@
+"""On-device edge construction: triples / adjacency tensors -> CSR, CSC and per-relation segments.
+
+Host-side mirror of what the reference does in Python before and inside the layers:
+  * GAT/models.py:141-148   nhop rows [s, r1, r2, t] -> edge_list_nhop=[t; s], edge_type_nhop=[r1, r2]
+  * GAT/layers.py:124-127   concatenate 1-hop then 2-hop edges
+  * GAT/layers.py:56-58     the coalesce-by-row hidden in sparse_coo_tensor + sparse.sum
+The aggregation key is edge[0] (= triple tail, GAT/preprocess.py:78-80); edge[1] is the gather index.
+All integer work runs in libspkbgat (spk_edges_concat, spk_sort_pairs, spk_segment_ptr, ...); torch is
+used for allocation and for the O(#hubs) task tables only.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+HUB_THRESH = 512      # segments longer than this are split ...
+HUB_CHUNK = 256       # ... into tasks of this many edges
+
+
+class HubSet:
+    """Task table for the segments of one ordering that exceed HUB_THRESH (see spk_hub_tasks)."""
+
+    def __init__(self, ptr, thresh=HUB_THRESH, chunk=HUB_CHUNK):
+        self.thresh = thresh
+        self.n_tasks = 0
+        self.n_hubs = 0
+        self.task_seg = self.task_beg = self.task_end = self.hub_seg = self.hub_task_ptr = None
+        if ptr.numel() <= 1:
+            return
+        ptr64 = ptr.long()
+        deg = ptr64[1:] - ptr64[:-1]
+        hub_seg = (deg > thresh).nonzero().flatten()
+        self.n_hubs = int(hub_seg.numel())
+        if self.n_hubs == 0:
+            return
+        ntask = (deg[hub_seg] + chunk - 1) // chunk
+        tptr = torch.zeros(self.n_hubs + 1, dtype=torch.int64, device=ptr.device)
+        tptr[1:] = torch.cumsum(ntask, 0)
+        self.n_tasks = int(tptr[-1].item())
+        task_hub = torch.repeat_interleave(torch.arange(self.n_hubs, device=ptr.device), ntask)
+        local = torch.arange(self.n_tasks, device=ptr.device) - tptr[task_hub]
+        seg = hub_seg[task_hub]
+        beg = ptr64[seg] + local * chunk
+        end = torch.minimum(beg + chunk, ptr64[seg + 1])
+        self.task_seg = seg.int().contiguous()
+        self.task_beg = beg.int().contiguous()
+        self.task_end = end.int().contiguous()
+        self.hub_seg = hub_seg.int().contiguous()
+        self.hub_task_ptr = tptr.int().contiguous()
+
+    def fill(self, hub, partial, ldpart):
+        """Populate a _lib.HubTasks struct; `partial` is the per-call scratch tensor (or None)."""
+        hub.n_tasks = self.n_tasks
+        hub.n_hubs = self.n_hubs
+        hub.hub_thresh = self.thresh
+        if self.n_tasks:
+            hub.task_seg = self.task_seg.data_ptr(); hub.task_beg = self.task_beg.data_ptr()
+            hub.task_end = self.task_end.data_ptr(); hub.hub_seg = self.hub_seg.data_ptr()
+            hub.hub_task_ptr = self.hub_task_ptr.data_ptr()
+            hub.partial = partial.data_ptr(); hub.ldpart = ldpart
+
+
+def _key_bits(n):
+    return max(1, int(n - 1).bit_length()) if n > 1 else 1
+
+
+def sort_pairs(keys, vals, key_bits):
+    """Stable radix sort by key of int32 (key, value) pairs on the device. Returns (keys, vals) sorted."""
+    lib = _lib.load()
+    n = keys.numel()
+    if n == 0:
+        return keys, vals
+    ktmp, vtmp = torch.empty_like(keys), torch.empty_like(vals)
+    ws = torch.empty(lib.spk_sort_workspace_bytes(n), dtype=torch.uint8, device=keys.device)
+    in_tmp = C.c_int32(0)
+    _lib.check(lib.spk_sort_pairs(keys.data_ptr(), vals.data_ptr(), ktmp.data_ptr(), vtmp.data_ptr(), n, key_bits,
+                                  ws.data_ptr(), C.byref(in_tmp), _lib.stream_ptr()), "sort_pairs")
+    return (ktmp, vtmp) if in_tmp.value else (keys, vals)
+
+
+def _iota(n, device):
+    v = torch.empty(n, dtype=torch.int32, device=device)
+    _lib.check(_lib.load().spk_iota_i32(v.data_ptr(), n, _lib.stream_ptr()), "iota")
+    return v
+
+
+def _gather(src, idx):
+    out = torch.empty(idx.numel(), dtype=torch.int32, device=src.device)
+    _lib.check(_lib.load().spk_gather_i32(src.data_ptr(), idx.data_ptr(), idx.numel(), out.data_ptr(),
+                                          _lib.stream_ptr()), "gather_i32")
+    return out
+
+
+def _segment_ptr(sorted_keys, n_seg):
+    ptr = torch.empty(n_seg + 1, dtype=torch.int32, device=sorted_keys.device)
+    _lib.check(_lib.load().spk_segment_ptr(sorted_keys.data_ptr() if sorted_keys.numel() else None,
+                                           sorted_keys.numel(), n_seg, ptr.data_ptr(), _lib.stream_ptr()), "segment_ptr")
+    return ptr
+
+
+class KGraph:
+    """Device-resident segment layouts of one edge list.
+
+    CSR  (key edge[0]) : rowptr[N+1], col[E], t1[E], t2[E]|None, perm[E] (CSR position -> original edge id),
+                         row[E] (aggregation row of each CSR position)
+    CSC  (key edge[1]) : colptr[Ncols+1], csc_row[E], csc_pos[E] (CSR position of the edge)
+    REL  (key relation): relptr[R+1], rel_row[M], rel_pos[M]   (2-hop edges appear under both relations)
+    """
+
+    def __init__(self, edge, edge_type, nhop, n_nodes, n_rel, device=None, n_cols=None, build_backward=True):
+        lib = _lib.load()
+        if device is None:
+            device = edge.device if edge.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self.n_nodes = int(n_nodes)
+        self.n_cols = int(n_cols if n_cols is not None else n_nodes)
+        self.n_rel = int(n_rel)
+        edge = edge.to(device=device, dtype=torch.int64).contiguous()
+        edge_type = edge_type.to(device=device, dtype=torch.int64).contiguous()
+        self.e1 = int(edge.shape[1]) if edge.dim() == 2 else 0
+        has2 = nhop is not None and nhop.numel() > 0
+        self.e2 = int(nhop.shape[0]) if has2 else 0
+        nhop = nhop.to(device=device, dtype=torch.int64).contiguous() if has2 else None
+        e = self.e1 + self.e2
+        self.n_edges = e
+        i32 = dict(dtype=torch.int32, device=device)
+        row = torch.empty(e, **i32); col = torch.empty(e, **i32); t1 = torch.empty(e, **i32)
+        t2 = torch.empty(e, **i32) if has2 else None
+        err = torch.zeros(1, **i32)
+        max_idx = max(self.n_nodes, self.n_cols)
+        _lib.check(lib.spk_edges_concat(edge.data_ptr() if self.e1 else None, self.e1,
+                                        edge_type.data_ptr() if self.e1 else None,
+                                        nhop.data_ptr() if has2 else None, self.e2,
+                                        row.data_ptr(), col.data_ptr(), t1.data_ptr(),
+                                        t2.data_ptr() if has2 else None, max_idx, self.n_rel,
+                                        err.data_ptr(), _lib.stream_ptr()), "edges_concat")
+        # CSR: stable sort by aggregation row
+        keys, perm = sort_pairs(row, _iota(e, device), _key_bits(max_idx))
+        if int(err.item()) != 0:
+            raise IndexError("edge / relation index out of range for the given entity / relation tables")
+        self.row = keys
+        self.perm = perm
+        self.rowptr = _segment_ptr(keys, self.n_nodes)
+        self.col = _gather(col, perm)
+        self.t1 = _gather(t1, perm)
+        self.t2 = _gather(t2, perm) if has2 else None
+        self.row_hubs = HubSet(self.rowptr)
+        self.colptr = self.csc_row = self.csc_pos = self.col_hubs = None
+        self.relptr = self.rel_row = self.rel_pos = self.rel_hubs = None
+        if build_backward:
+            self.build_backward()
+
+    def build_backward(self):
+        if self.colptr is not None:
+            return
+        lib = _lib.load()
+        e, device = self.n_edges, self.device
+        ckeys, cpos = sort_pairs(self.col.clone(), _iota(e, device), _key_bits(self.n_cols))
+        self.colptr = _segment_ptr(ckeys, self.n_cols)
+        self.csc_pos = cpos
+        self.csc_row = _gather(self.row, cpos)
+        self.col_hubs = HubSet(self.colptr)
+        m = 2 * e if self.t2 is not None else e
+        rkeys = torch.empty(m, dtype=torch.int32, device=device)
+        rvals = torch.empty(m, dtype=torch.int32, device=device)
+        _lib.check(lib.spk_rel_incidence(self.t1.data_ptr(), self.t2.data_ptr() if self.t2 is not None else None,
+                                         e, self.n_rel, rkeys.data_ptr(), rvals.data_ptr(), _lib.stream_ptr()),
+                   "rel_incidence")
+        rkeys, rpos = sort_pairs(rkeys, rvals, _key_bits(self.n_rel + 1))
+        self.relptr = _segment_ptr(rkeys, self.n_rel)
+        self.rel_pos = rpos
+        self.rel_row = _gather(self.row, rpos)
+        self.rel_hubs = HubSet(self.relptr)
+
+    def to_csr_order(self, per_edge):
+        """Reorder a per-edge tensor given in the caller's edge order ([..., E]) into CSR order."""
+        return per_edge.index_select(-1, self.perm.long()).contiguous()

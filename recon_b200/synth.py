@@ -3,7 +3,7 @@
 edge[1] (gather index = triple head) is uniform; edge[0] (aggregation row = triple tail,
 GAT/preprocess.py:78-80) is Zipf: rank = floor(Pareto(x_m=1, alpha)) mapped through a fixed
 random permutation of [0, N) and clipped to N-1; relation types are uniform. Edge order is
-generation order (unsorted). CPU generation (torch.Generator) so every rank, the oracle and
+generation order (unsorted). CPU generation (torch.Generator) so every rank, the CPU checker and
 the CUDA path see identical inputs.
 """
 import math

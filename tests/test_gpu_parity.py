@@ -1,0 +1,313 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes), against the golden
+fixtures produced by the reference and against the CPU oracle on seeded inputs.
+
+Tolerance: north_star asks rel-err <= 1e-4 on outputs and gradients against the reference fp32 path; we
+compare against the reference's fp64 run (tests/golden, or oracle in fp64) with rel-L2 <= 1e-4 and
+additionally expect ~1e-6 because every product is fp32-exact (SURVEY.md 8c calibration)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, rel_l2, golden_params, golden_masks, MODEL_CASES
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # north_star tolerance
+TIGHT = 2e-5        # what fp32-exact kernels should reach
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def build_model(g, p_drop=0.0):
+    from recon_b200 import SpKBGATModified
+    p = golden_params(g)
+    n, f = p["entity_embeddings"].shape
+    r = p["relation_embeddings"].shape[0]
+    heads = sum(1 for k in p if k.startswith("sparse_gat_1.attention_") and k.endswith(".a"))
+    d = p["sparse_gat_1.attention_0.a"].shape[0]
+    m = SpKBGATModified(p["entity_embeddings"].clone(), p["relation_embeddings"].clone(), [d, 2 * d], [d, 2 * d],
+                        p_drop, 0.2, [heads, heads], None)
+    m.load_state_dict(p)
+    return m.to(dev())
+
+
+# ---- K0: graph construction ----------------------------------------------------------------------
+@pytest.mark.parametrize("n,bits", [(0, 5), (1, 1), (33, 3), (5000, 13), (300000, 21), (1 << 20, 31)])
+def test_radix_sort_pairs_is_stable_and_exact(n, bits):
+    from recon_b200.graph import sort_pairs
+    g = torch.Generator().manual_seed(n)
+    keys = torch.randint(0, 1 << min(bits, 30), (n,), generator=g, dtype=torch.int32)
+    vals = torch.arange(n, dtype=torch.int32)
+    k2, v2 = sort_pairs(keys.to(dev()).clone(), vals.to(dev()).clone(), bits)
+    ks, order = torch.sort(keys, stable=True)
+    assert torch.equal(k2.cpu(), ks)
+    assert torch.equal(v2.cpu().long(), order)
+
+
+@pytest.mark.parametrize("alpha,n_nhop", [(None, 0), (1.1, 700), (1.5, 0)])
+def test_kgraph_layouts_bit_exact(alpha, n_nhop):
+    from recon_b200 import KGraph
+    from recon_b200.synth import make_kg
+    n, e, r = 3000, 40000, 17
+    edge, etype, nhop = make_kg(n, e, r, alpha, n_nhop, seed=5)
+    g = KGraph(edge, etype, nhop, n, r, device=dev())
+    rows = torch.cat((edge[0], nhop[:, 3])); cols = torch.cat((edge[1], nhop[:, 0]))
+    t1 = torch.cat((etype, nhop[:, 1])); t2 = torch.cat((torch.full((e,), -1, dtype=torch.long), nhop[:, 2]))
+    srow, perm = torch.sort(rows, stable=True)
+    assert torch.equal(g.perm.cpu().long(), perm)
+    assert torch.equal(g.row.cpu().long(), srow)
+    assert torch.equal(g.col.cpu().long(), cols[perm])
+    assert torch.equal(g.t1.cpu().long(), t1[perm])
+    if n_nhop:
+        assert torch.equal(g.t2.cpu().long(), t2[perm])
+    else:
+        assert g.t2 is None
+    rowptr = torch.searchsorted(srow, torch.arange(n + 1))
+    assert torch.equal(g.rowptr.cpu().long(), rowptr)
+    ccol, cpos = torch.sort(cols[perm], stable=True)
+    assert torch.equal(g.csc_pos.cpu().long(), cpos)
+    assert torch.equal(g.csc_row.cpu().long(), srow[cpos])
+    assert torch.equal(g.colptr.cpu().long(), torch.searchsorted(ccol, torch.arange(n + 1)))
+    # relation incidence: every (relation, edge) pair exactly once, segments stable
+    relptr = g.relptr.cpu().long(); rpos = g.rel_pos.cpu().long()
+    t1c, t2c = t1[perm], t2[perm]
+    for k in range(r):
+        seg = rpos[relptr[k]:relptr[k + 1]]
+        want = torch.cat(((t1c == k).nonzero().flatten(), (t2c == k).nonzero().flatten()))
+        assert torch.equal(seg, want)
+    # hub tasks tile every hub segment exactly
+    hubs = g.row_hubs
+    deg = rowptr[1:] - rowptr[:-1]
+    assert hubs.n_hubs == int((deg > hubs.thresh).sum())
+    if hubs.n_tasks:
+        tb, te, ts = hubs.task_beg.cpu().long(), hubs.task_end.cpu().long(), hubs.task_seg.cpu().long()
+        assert int((te - tb).sum()) == int(deg[deg > hubs.thresh].sum())
+        assert bool(((tb >= rowptr[ts]) & (te <= rowptr[ts + 1]) & (te > tb)).all())
+
+
+def test_kgraph_rejects_out_of_range():
+    from recon_b200 import KGraph
+    edge = torch.tensor([[0, 5], [1, 2]]); et = torch.tensor([0, 0])
+    with pytest.raises(IndexError):
+        KGraph(edge, et, None, 4, 2, device=dev())
+    with pytest.raises(IndexError):
+        KGraph(torch.tensor([[0, 1], [1, 2]]), torch.tensor([0, 3]), None, 4, 2, device=dev())
+
+
+def test_kgraph_empty():
+    from recon_b200 import KGraph
+    g = KGraph(torch.zeros(2, 0, dtype=torch.long), torch.zeros(0, dtype=torch.long), None, 7, 3, device=dev())
+    assert g.rowptr.cpu().tolist() == [0] * 8 and g.colptr.cpu().tolist() == [0] * 8
+
+
+# ---- K1/K5: GEMMs ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (130, 50, 416), (1000, 200, 416), (257, 416, 50), (3, 7, 5), (4096, 64, 200)])
+def test_gemm_nn(m, k, n):
+    from recon_b200.functional import gemm_nn
+    g = torch.Generator().manual_seed(m + k + n)
+    a = torch.randn(m, k, generator=g); b = torch.randn(k, n, generator=g)
+    c = gemm_nn(a.to(dev()), b.to(dev()))
+    assert rel_l2(c, a.double() @ b.double()) < 2e-6
+    c0 = torch.randn(m, n, generator=g)
+    c2 = gemm_nn(a.to(dev()), b.to(dev()), out=c0.to(dev()), accumulate=True)
+    assert rel_l2(c2, c0.double() + a.double() @ b.double()) < 2e-6
+
+
+def test_gemm_nn_strided_views():
+    from recon_b200.functional import gemm_nn
+    g = torch.Generator().manual_seed(0)
+    big = torch.randn(300, 96, generator=g).to(dev()); b = torch.randn(40, 24, generator=g).to(dev())
+    a = big[:, 8:48]
+    out = torch.zeros(300, 64, device=dev())
+    gemm_nn(a, b, out=out[:, 16:40])
+    assert rel_l2(out[:, 16:40], a.double().cpu() @ b.double().cpu()) < 2e-6
+    assert float(out[:, :16].abs().sum()) == 0.0 and float(out[:, 40:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("m,ka,nb", [(1, 1, 1), (5000, 50, 416), (70000, 200, 416), (333, 7, 5), (100000, 11, 208)])
+def test_gemm_tn_deterministic(m, ka, nb):
+    from recon_b200.functional import gemm_tn
+    g = torch.Generator().manual_seed(m)
+    a = torch.randn(m, ka, generator=g); b = torch.randn(m, nb, generator=g)
+    c = gemm_tn(a.to(dev()), b.to(dev()))
+    assert rel_l2(c, a.double().t() @ b.double()) < 5e-6
+    c2 = gemm_tn(a.to(dev()), b.to(dev()))
+    assert torch.equal(c, c2)
+
+
+# ---- stand-alone op and layer ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["spmm_f1", "spmm_f7"])
+def test_special_spmm_golden(name):
+    from recon_b200 import SpecialSpmmFunctionFinal
+    g = load_golden(name)
+    w = torch.as_tensor(g["w"]).to(dev()).requires_grad_(True)
+    n, f = g["out"].shape
+    out = SpecialSpmmFunctionFinal.apply(torch.as_tensor(g["edge"]), w, n, w.shape[0], f)
+    (out * torch.as_tensor(g["g"]).to(dev())).sum().backward()
+    assert rel_l2(out, g["out"]) < 1e-6
+    assert np.array_equal(w.grad.cpu().numpy(), g["grad_w"])
+
+
+@pytest.mark.parametrize("name", ["layer_concat", "layer_noconcat_nhop"])
+def test_attention_layer_golden(name):
+    from recon_b200 import SpGraphAttentionLayer
+    g = load_golden(name)
+    n, f = g["x"].shape
+    d, k = g["a"].shape
+    layer = SpGraphAttentionLayer(n, f, d, k - 2 * f, 0.0, 0.2, bool(g["concat"])).to(dev())
+    with torch.no_grad():
+        layer.a.copy_(torch.as_tensor(g["a"])); layer.a_2.copy_(torch.as_tensor(g["a_2"]))
+    x = torch.as_tensor(g["x"]).to(dev()).requires_grad_(True)
+    emb = torch.as_tensor(g["edge_embed"]).to(dev()).requires_grad_(True)
+    has2 = g["edge_nhop"].size > 0
+    e2 = torch.as_tensor(g["edge_nhop"]).long() if has2 else torch.tensor([])
+    emb2 = torch.as_tensor(g["edge_embed_nhop"]).to(dev()).requires_grad_(True) if has2 else torch.tensor([])
+    out = layer(x, torch.as_tensor(g["edge"]), emb, e2, emb2)
+    (out * torch.as_tensor(g["g"]).to(dev())).sum().backward()
+    assert rel_l2(out, g["out"]) < TIGHT
+    assert rel_l2(x.grad, g["grad.x"]) < TIGHT
+    assert rel_l2(emb.grad, g["grad.edge_embed"]) < TIGHT
+    assert rel_l2(layer.a.grad, g["grad.a"]) < TIGHT
+    assert rel_l2(layer.a_2.grad, g["grad.a_2"]) < TIGHT
+    if has2:
+        assert rel_l2(emb2.grad, g["grad.edge_embed_nhop"]) < TIGHT
+
+
+# ---- full model against the reference's own outputs ---------------------------------------------------
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_model_golden(name):
+    g = load_golden(name)
+    model = build_model(g, float(g["p_drop"]))
+    masks = golden_masks(g)
+    adj = (torch.as_tensor(g["edge"]), torch.as_tensor(g["edge_type"]))
+    nhop = torch.as_tensor(g["nhop"])
+    be = torch.as_tensor(g["batch_entities"])
+    ge, gr = torch.as_tensor(g["g_ent"]).to(dev()), torch.as_tensor(g["g_rel"]).to(dev())
+    if name == "model_batch_test":
+        out_e, out_r, mask = model.batch_test(None, be, adj, nhop, torch.as_tensor(g["entity_in"]).to(dev()),
+                                              dropout_masks=masks)
+    else:
+        out_e, out_r, mask = model(None, be, adj, nhop, dropout_masks=masks)
+    ((out_e * ge).sum() + (out_r * gr).sum()).backward()
+    errs = {"out_entity": rel_l2(out_e, g["f64.out_entity"]), "out_relation": rel_l2(out_r, g["f64.out_relation"])}
+    assert np.array_equal(mask.cpu().numpy(), g["f64.mask"].astype(np.float32))
+    n_grads = 0
+    for k, v in g.items():
+        if k.startswith("f64.grad."):
+            nm = k[len("f64.grad."):]
+            prm = dict(model.named_parameters())[nm]
+            assert prm.grad is not None, nm
+            errs["grad." + nm] = rel_l2(prm.grad, v)
+            n_grads += 1
+    assert n_grads >= 5
+    if name != "model_batch_test":      # the three .data side effects (models.py:160-161,181-183)
+        errs["after.entity_embeddings"] = rel_l2(model.entity_embeddings.data, g["f64.after.entity_embeddings"])
+        errs["after.final_entity"] = rel_l2(model.final_entity_embeddings.data, g["f64.after.final_entity_embeddings"])
+        errs["after.final_relation"] = rel_l2(model.final_relation_embeddings.data, g["f64.after.final_relation_embeddings"])
+    bad = {k: v for k, v in errs.items() if not v < TIGHT}
+    assert not bad, bad
+    # and against the reference's fp32 numbers at the north_star tolerance
+    assert rel_l2(out_e, g["f32.out_entity"]) < TOL and rel_l2(out_r, g["f32.out_relation"]) < TOL
+
+
+def test_state_dict_keys_match_reference():
+    g = load_golden("model_small_uniform")
+    model = build_model(g)
+    want = {k[len("param."):]: v.shape for k, v in g.items() if k.startswith("param.")}
+    got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    assert got == {k: tuple(s) for k, s in want.items()}
+
+
+# ---- seeded synthetic inputs against the oracle (C1 shape, uniform and Zipf with hub rows) ------------
+@pytest.mark.parametrize("alpha,n_nhop,p_drop", [(None, 0, 0.0), (1.1, 0, 0.0), (1.1, 20000, 0.3)])
+def test_model_vs_oracle_c1(alpha, n_nhop, p_drop):
+    from recon_b200 import SpKBGATModified
+    from recon_b200.synth import make_kg
+    from oracle import ref_torch as O
+    n, e, r, f, d, h = 10000, 100000, 200, 50, 100, 2
+    edge, etype, nhop = make_kg(n, e, r, alpha, n_nhop, seed=11)
+    p = O.init_params(n, r, f, d, h, seed=11)
+    gen = torch.Generator().manual_seed(12)
+    ge, gr = torch.randn(n, d * h, generator=gen), torch.randn(r, d * h, generator=gen)
+    masks = None
+    if p_drop > 0:
+        et = e + n_nhop
+        mk = lambda *s: (torch.rand(*s, generator=gen) >= p_drop).float() / (1 - p_drop)   # noqa: E731
+        masks = {"att": mk(h, et), "out": mk(et), "x": mk(n, d * h)}
+    be = torch.arange(0, n, 3)
+    model = SpKBGATModified(p["entity_embeddings"].clone(), p["relation_embeddings"].clone(), [d, 2 * d], [d, 2 * d],
+                            p_drop, 0.2, [h, h], None)
+    model.load_state_dict(p)
+    model = model.to(dev())
+    out_e, out_r, mask = model(None, be, (edge, etype), nhop, dropout_masks=masks)
+    ((out_e * ge.to(dev())).sum() + (out_r * gr.to(dev())).sum()).backward()
+    p64 = {k: v.double() for k, v in p.items()}
+    m64 = None if masks is None else {k: v.double() for k, v in masks.items()}
+    ref = O.fwd_bwd(p64, be, (edge, etype), nhop, 0.2, ge.double(), gr.double(), m64, O.seg_sum_index_add)
+    errs = {"out_entity": rel_l2(out_e, ref[0]), "out_relation": rel_l2(out_r, ref[1])}
+    for nm, prm in model.named_parameters():
+        if nm in ref[4]:
+            errs["grad." + nm] = rel_l2(prm.grad, ref[4][nm])
+    assert len(errs) >= 10
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, bad
+    if alpha is not None:
+        assert model.prepare_graph((edge, etype), nhop).row_hubs.n_hubs > 0      # the hub path was exercised
+
+
+def test_run_to_run_bit_identical():
+    from recon_b200 import SpKBGATModified
+    from recon_b200.synth import make_kg
+    from oracle import ref_torch as O
+    n, e, r = 4000, 60000, 31
+    edge, etype, nhop = make_kg(n, e, r, 1.1, 5000, seed=3)
+    p = O.init_params(n, r, 50, 100, 2, seed=3)
+    outs = []
+    for _ in range(2):
+        model = SpKBGATModified(p["entity_embeddings"].clone(), p["relation_embeddings"].clone(), [100, 200],
+                                [100, 200], 0.0, 0.2, [2, 2], None)
+        model.load_state_dict(p)
+        model = model.to(dev())
+        oe, orel, _ = model(None, torch.arange(n), (edge, etype), nhop)
+        (oe.sum() + orel.sum()).backward()
+        outs.append([oe.detach().clone()] + [prm.grad.clone() for prm in model.parameters() if prm.grad is not None])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_overflow_raises_assertion_like_reference():
+    """exp without max-subtraction (GAT/layers.py:143-146): huge scores overflow to inf -> NaN -> AssertionError."""
+    from recon_b200 import SpKBGATModified
+    from recon_b200.synth import make_kg
+    from oracle import ref_torch as O
+    n, e, r = 200, 2000, 5
+    edge, etype, nhop = make_kg(n, e, r, None, 0, seed=1)
+    p = O.init_params(n, r, 12, 8, 2, seed=1)
+    p["relation_embeddings"] = p["relation_embeddings"] * 1e4
+    model = SpKBGATModified(p["entity_embeddings"].clone(), p["relation_embeddings"].clone(), [8, 16], [8, 16], 0.0,
+                            0.2, [2, 2], None)
+    model.load_state_dict(p)
+    model = model.to(dev())
+    with pytest.raises(AssertionError):
+        model(None, torch.arange(n), (edge, etype), nhop)
+
+
+def test_training_mode_dropout_runs_and_is_unbiased_in_shape():
+    from recon_b200 import SpKBGATModified
+    from recon_b200.synth import make_kg
+    from oracle import ref_torch as O
+    n, e, r = 300, 3000, 7
+    edge, etype, nhop = make_kg(n, e, r, 1.5, 100, seed=2)
+    p = O.init_params(n, r, 12, 8, 2, seed=2)
+    model = SpKBGATModified(p["entity_embeddings"].clone(), p["relation_embeddings"].clone(), [8, 16], [8, 16], 0.3,
+                            0.2, [2, 2], None)
+    model.load_state_dict(p)
+    model = model.to(dev()).train()
+    oe, orel, _ = model(None, torch.arange(n), (edge, etype), nhop)
+    (oe.sum() + orel.sum()).backward()
+    assert torch.isfinite(oe).all() and all(torch.isfinite(q.grad).all() for q in model.parameters() if q.grad is not None)
+    model.eval()
+    a = model(None, torch.arange(n), (edge, etype), nhop)[0]
+    b = model(None, torch.arange(n), (edge, etype), nhop)[0]
+    assert torch.equal(a, b)
