@@ -76,6 +76,13 @@ int64_t spk_gemm_tn_workspace_floats(int64_t M, int32_t Ka, int32_t Nb);
 int spk_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                 int64_t M, int32_t Ka, int32_t Nb, int32_t accumulate, float* workspace, spk_stream_t stream);
 
+/* Same product on the tcgen05 tensor cores: 3xTF32 error-compensated (fp32-accurate), TMA-fed, TMEM accumulators.
+ * Needs A 16-byte aligned with lda % 4 == 0 (spk_gemm_nn_tc_supported) and 2*N*roundup(K,4) floats of workspace. */
+int32_t spk_gemm_nn_tc_supported(const float* A, int64_t lda, int64_t M, int32_t N, int32_t K);
+int64_t spk_gemm_tc_workspace_floats(int32_t N, int32_t K);
+int spk_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int32_t N, int32_t K, int32_t accumulate, float* workspace, spk_stream_t stream);
+
 /* ---- K2: fused attention forward (replaces SpGraphAttentionLayer.forward layers.py:124-175 for all
  *      heads of a group, incl. both SpecialSpmmFinal calls, the divide and the ELU) ---- */
 typedef struct {

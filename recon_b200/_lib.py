@@ -76,6 +76,9 @@ SIGNATURES = {
     "spk_gather_i32": (_I32, [_VP, _VP, _I64, _VP, _VP]),
     "spk_rel_incidence": (_I32, [_VP, _VP, _I64, _I32, _VP, _VP, _VP]),
     "spk_gemm_nn": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP]),
+    "spk_gemm_nn_tc_supported": (_I32, [_VP, _I64, _I64, _I32, _I32]),
+    "spk_gemm_tc_workspace_floats": (_I64, [_I32, _I32]),
+    "spk_gemm_nn_tc": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
     "spk_gemm_tn_workspace_floats": (_I64, [_I64, _I32, _I32]),
     "spk_gemm_tn": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
     "spk_edge_attn_fwd": (_I32, [C.POINTER(EdgeFwdArgs), _VP]),
@@ -103,7 +106,7 @@ class _Lib:
 
     def __getattr__(self, name):
         fn = getattr(self._cdll, name)
-        if self.timing is None or SIGNATURES[name][1][-1:] != [_VP] or name.startswith("spk_gemm_tn_w"):
+        if self.timing is None or SIGNATURES[name][1][-1:] != [_VP] or "workspace" in name or "supported" in name:
             return fn
 
         def timed(*args):

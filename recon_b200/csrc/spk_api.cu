@@ -130,6 +130,18 @@ int spk_gemm_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float*
     return gemm_tn_simt(A, lda, B, ldb, C, ldc, M, Ka, Nb, accumulate, workspace, (cudaStream_t)stream);
 }
 
+int32_t spk_gemm_nn_tc_supported(const float* A, int64_t lda, int64_t M, int32_t N, int32_t K) {
+    return gemm_nn_tc_supported(A, lda, M, N, K);
+}
+int64_t spk_gemm_tc_workspace_floats(int32_t N, int32_t K) { return 2LL * N * gemm_tc_ldt(K); }
+int spk_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int32_t N, int32_t K, int32_t accumulate, float* workspace, spk_stream_t stream) {
+    if (lda < K || ldb < N || ldc < N) { set_error("gemm_nn_tc: leading dimension too small"); return 1; }
+    if (!gemm_nn_tc_supported(A, lda, M, N, K)) { set_error("gemm_nn_tc: A must be 16-byte aligned with lda %% 4 == 0"); return 1; }
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15)) { set_error("gemm_nn_tc: aligned workspace required"); return 1; }
+    return gemm_nn_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, workspace, (cudaStream_t)stream);
+}
+
 int spk_edge_attn_fwd(const spk_edge_fwd_args* p, spk_stream_t stream) {
     EdgeFwdArgs a;
     if (!geom_ok(p->geom, &a.g, "edge_attn_fwd")) return 1;

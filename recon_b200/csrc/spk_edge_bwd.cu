@@ -26,32 +26,34 @@ __device__ __forceinline__ float4 load_act_chunk(const float* base, int h, int o
     return r;
 }
 
-template <int NCH>
+template <int NCH, int HT>
 struct RowCtx {
     float4 dnum[NCH];
     int hc[NCH];
-    float q1[SPK_MAX_HEADS];
-    float dden[SPK_MAX_HEADS];
-    float c1[SPK_MAX_HEADS];       // dnum . P1[i] per head
+    float q1[HT];
+    float dden[HT];
+    float c1[HT];       // dnum . P1[i] per head
 };
 
-template <int NCH>
-__device__ __forceinline__ void bwd_row_prologue(const EdgeBwdRowsArgs& a, int row, int lane, RowCtx<NCH>& rc) {
+template <int NCH, int HT>
+__device__ __forceinline__ void bwd_row_prologue(const EdgeBwdRowsArgs& a, int row, int lane, RowCtx<NCH, HT>& rc) {
     const LayerGeom g = a.g;
-    float pdh[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
-    float pc1[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
-    float den[SPK_MAX_HEADS];
+    float pdh[HT], pc1[HT], den[HT];
 #pragma unroll
-    for (int h = 0; h < SPK_MAX_HEADS; ++h) den[h] = h < g.H ? __ldg(a.den + (long)row * g.H + h) : 1.f;
+    for (int h = 0; h < HT; ++h) {
+        pdh[h] = 0.f; pc1[h] = 0.f;
+        den[h] = h < g.H ? __ldg(a.den + (long)row * g.H + h) : 1.f;
+    }
     const float4 q1v = ldg4(a.P1 + (long)row * a.ld1 + (long)g.Dt4 * 4);
-    rc.q1[0] = q1v.x; rc.q1[1] = q1v.y; rc.q1[2] = q1v.z; rc.q1[3] = q1v.w;
+#pragma unroll
+    for (int h = 0; h < HT; ++h) rc.q1[h] = f4get(q1v, h);
 #pragma unroll
     for (int ci = 0; ci < NCH; ++ci) {
         const int c4 = lane + 32 * ci;
         rc.hc[ci] = 0;
         rc.dnum[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c4 >= g.Dt4) continue;
-        const int h = c4 / g.Dp4;
+        const int h = HT > 1 ? c4 / g.Dp4 : 0;
         rc.hc[ci] = h;
         const int off = (c4 - h * g.Dp4) * 4;
         const float4 o4 = load_act_chunk(a.out + (long)row * a.ldo, h, off, g.D, a.out_vec);
@@ -71,19 +73,19 @@ __device__ __forceinline__ void bwd_row_prologue(const EdgeBwdRowsArgs& a, int r
                 hv[k] = o[k];
             }
         }
-        const float d = sel4(h, den[0], den[1], den[2], den[3]);
+        const float d = selh<HT>(h, den);
         const float dot_h = fmaf(dh[0], hv[0], fmaf(dh[1], hv[1], fmaf(dh[2], hv[2], dh[3] * hv[3])));
         rc.dnum[ci] = make_float4(dh[0] / d, dh[1] / d, dh[2] / d, dh[3] / d);
         const float4 p1 = ldg4(a.P1 + (long)row * a.ld1 + c4 * 4);
         const float dot_c = f4dot(rc.dnum[ci], p1);
 #pragma unroll
-        for (int hh = 0; hh < SPK_MAX_HEADS; ++hh) {
+        for (int hh = 0; hh < HT; ++hh) {
             pdh[hh] += (h == hh) ? dot_h : 0.f;
             pc1[hh] += (h == hh) ? dot_c : 0.f;
         }
     }
 #pragma unroll
-    for (int h = 0; h < SPK_MAX_HEADS; ++h) {
+    for (int h = 0; h < HT; ++h) {
         rc.dden[h] = 0.f; rc.c1[h] = 0.f;
         if (h < g.H) {
             rc.dden[h] = -warp_sum(pdh[h]) / den[h];
@@ -92,10 +94,10 @@ __device__ __forceinline__ void bwd_row_prologue(const EdgeBwdRowsArgs& a, int r
     }
 }
 
-template <int NCH, bool HAS2>
+template <int NCH, int HT, bool HAS2>
 __device__ __forceinline__ void bwd_row_edges(const EdgeBwdRowsArgs& a, int beg, int end, int lane,
-                                              const RowCtx<NCH>& rc, float (&usum)[SPK_MAX_HEADS],
-                                              float (&swsum)[SPK_MAX_HEADS]) {
+                                              const RowCtx<NCH, HT>& rc, float (&usum)[HT],
+                                              float (&swsum)[HT]) {
     constexpr int U = (NCH <= 2) ? 4 : 2;
     const LayerGeom g = a.g;
     const int qlane = g.Dt4 & 31, qci = g.Dt4 >> 5;
@@ -103,15 +105,16 @@ __device__ __forceinline__ void bwd_row_edges(const EdgeBwdRowsArgs& a, int beg,
     for (int base = beg; base < end; base += 32) {
         const int n = min(32, end - base);
         int my_col = 0, my_t1 = 0, my_t2 = -1;
-        float my_m[SPK_MAX_HEADS] = {1.f, 1.f, 1.f, 1.f};
-        float my_w[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, my_ds[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+        float my_m[HT], my_w[HT], my_ds[HT];
+#pragma unroll
+        for (int h = 0; h < HT; ++h) { my_m[h] = 1.f; my_w[h] = 0.f; my_ds[h] = 0.f; }
         if (lane < n) {
             my_col = __ldg(a.col + base + lane);
             my_t1 = __ldg(a.t1 + base + lane);
             if (HAS2) my_t2 = __ldg(a.t2 + base + lane);
             if (has_mask) {
 #pragma unroll
-                for (int h = 0; h < SPK_MAX_HEADS; ++h)
+                for (int h = 0; h < HT; ++h)
                     if (h < g.H) my_m[h] = __ldg(a.mask + (long)h * a.mask_stride + base + lane);
             }
         }
@@ -146,15 +149,17 @@ __device__ __forceinline__ void bwd_row_edges(const EdgeBwdRowsArgs& a, int beg,
 #pragma unroll
                 for (int ci = 1; ci < NCH; ++ci)
                     if (qci == ci) qv = v[u][ci];
-                float pd[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
+                float pd[HT];
+#pragma unroll
+                for (int h = 0; h < HT; ++h) pd[h] = 0.f;
 #pragma unroll
                 for (int ci = 0; ci < NCH; ++ci) {
                     const float d = f4dot(rc.dnum[ci], v[u][ci]);     // dnum is 0 on q / pad chunks
 #pragma unroll
-                    for (int h = 0; h < SPK_MAX_HEADS; ++h) pd[h] += (rc.hc[ci] == h) ? d : 0.f;
+                    for (int h = 0; h < HT; ++h) pd[h] += (HT == 1 || rc.hc[ci] == h) ? d : 0.f;
                 }
 #pragma unroll
-                for (int h = 0; h < SPK_MAX_HEADS; ++h) {
+                for (int h = 0; h < HT; ++h) {
                     if (h < g.H) {
                         const float t = rc.c1[h] + warp_sum(pd[h]);
                         const float s = rc.q1[h] + __shfl_sync(0xffffffffu, f4get(qv, h), qlane);
@@ -174,15 +179,15 @@ __device__ __forceinline__ void bwd_row_edges(const EdgeBwdRowsArgs& a, int beg,
         if (lane < n) {
             float* r = a.rec + (long)(base + lane) * (2 * g.H);
 #pragma unroll
-            for (int h = 0; h < SPK_MAX_HEADS; ++h)
+            for (int h = 0; h < HT; ++h)
                 if (h < g.H) *reinterpret_cast<float2*>(r + 2 * h) = make_float2(my_w[h], my_ds[h]);
         }
     }
 }
 
-template <int NCH>
-__device__ __forceinline__ void bwd_row_store(const EdgeBwdRowsArgs& a, int row, int lane, const RowCtx<NCH>& rc,
-                                              const float (&usum)[SPK_MAX_HEADS], const float (&swsum)[SPK_MAX_HEADS],
+template <int NCH, int HT>
+__device__ __forceinline__ void bwd_row_store(const EdgeBwdRowsArgs& a, int row, int lane, const RowCtx<NCH, HT>& rc,
+                                              const float (&usum)[HT], const float (&swsum)[HT],
                                               bool store_g, bool store_dp1) {
     const LayerGeom g = a.g;
 #pragma unroll
@@ -193,10 +198,11 @@ __device__ __forceinline__ void bwd_row_store(const EdgeBwdRowsArgs& a, int row,
         if (store_dp1 && c4 < g.Wd4) {
             float4 o;
             if (c4 < g.Dt4) {
-                const float s = sel4(rc.hc[ci], swsum[0], swsum[1], swsum[2], swsum[3]);
+                const float s = selh<HT>(rc.hc[ci], swsum);
                 o = make_float4(s * rc.dnum[ci].x, s * rc.dnum[ci].y, s * rc.dnum[ci].z, s * rc.dnum[ci].w);
             } else if (c4 == g.Dt4) {
-                o = make_float4(usum[0], usum[1], usum[2], usum[3]);
+                o = make_float4(usum[0], HT > 1 ? usum[HT > 1 ? 1 : 0] : 0.f, HT > 2 ? usum[HT > 2 ? 2 : 0] : 0.f,
+                                HT > 3 ? usum[HT > 3 ? 3 : 0] : 0.f);
             } else {
                 o = make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -205,85 +211,95 @@ __device__ __forceinline__ void bwd_row_store(const EdgeBwdRowsArgs& a, int row,
     }
 }
 
-template <int NCH, bool HAS2>
-__global__ void __launch_bounds__(SPK_CTA_THREADS)
+template <int NCH, int HT, bool HAS2>
+__global__ void __launch_bounds__(SPK_CTA_THREADS, (NCH <= 2) ? 3 : 2)
 edge_bwd_rows_kernel(const EdgeBwdRowsArgs a) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (row >= a.n_rows) return;
     const int beg = __ldg(a.segptr + row), end = __ldg(a.segptr + row + 1);
     if (end - beg > a.hub.hub_thresh) return;
-    RowCtx<NCH> rc;
-    bwd_row_prologue<NCH>(a, row, lane, rc);
-    float usum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, swsum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
-    bwd_row_edges<NCH, HAS2>(a, beg, end, lane, rc, usum, swsum);
-    bwd_row_store<NCH>(a, row, lane, rc, usum, swsum, true, true);
+    RowCtx<NCH, HT> rc;
+    bwd_row_prologue<NCH, HT>(a, row, lane, rc);
+    float usum[HT], swsum[HT];
+#pragma unroll
+    for (int h = 0; h < HT; ++h) usum[h] = swsum[h] = 0.f;
+    bwd_row_edges<NCH, HT, HAS2>(a, beg, end, lane, rc, usum, swsum);
+    bwd_row_store<NCH, HT>(a, row, lane, rc, usum, swsum, true, true);
 }
 
-template <int NCH, bool HAS2>
-__global__ void __launch_bounds__(SPK_CTA_THREADS)
+template <int NCH, int HT, bool HAS2>
+__global__ void __launch_bounds__(SPK_CTA_THREADS, (NCH <= 2) ? 3 : 2)
 edge_bwd_rows_tasks_kernel(const EdgeBwdRowsArgs a) {
     const int lane = threadIdx.x & 31;
     const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (task >= a.hub.n_tasks) return;
     const int row = __ldg(a.hub.task_seg + task);
-    RowCtx<NCH> rc;
-    bwd_row_prologue<NCH>(a, row, lane, rc);
-    float usum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, swsum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
-    bwd_row_edges<NCH, HAS2>(a, __ldg(a.hub.task_beg + task), __ldg(a.hub.task_end + task), lane, rc, usum, swsum);
+    RowCtx<NCH, HT> rc;
+    bwd_row_prologue<NCH, HT>(a, row, lane, rc);
+    float usum[HT], swsum[HT];
+#pragma unroll
+    for (int h = 0; h < HT; ++h) usum[h] = swsum[h] = 0.f;
+    bwd_row_edges<NCH, HT, HAS2>(a, __ldg(a.hub.task_beg + task), __ldg(a.hub.task_end + task), lane, rc, usum, swsum);
     if (lane < SPK_MAX_HEADS) {
         float* part = a.hub.partial + (long)task * a.hub.ldpart;
-        part[lane] = sel4(lane, usum[0], usum[1], usum[2], usum[3]);
-        part[SPK_MAX_HEADS + lane] = sel4(lane, swsum[0], swsum[1], swsum[2], swsum[3]);
+        part[lane] = lane < HT ? selh<HT>(lane, usum) : 0.f;
+        part[SPK_MAX_HEADS + lane] = lane < HT ? selh<HT>(lane, swsum) : 0.f;
     }
 }
 
-template <int NCH>
+// one CTA per hub row; see edge_fwd_hub_finalize_kernel for the summation order
+template <int NCH, int HT>
 __global__ void __launch_bounds__(SPK_CTA_THREADS)
 edge_bwd_rows_hub_finalize_kernel(const EdgeBwdRowsArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int hub = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (hub >= a.hub.n_hubs) return;
+    __shared__ float red[SPK_WARPS_PER_CTA][2 * SPK_MAX_HEADS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int hub = blockIdx.x;
     const int row = __ldg(a.hub.hub_seg + hub);
-    RowCtx<NCH> rc;
-    bwd_row_prologue<NCH>(a, row, lane, rc);
-    float usum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f}, swsum[SPK_MAX_HEADS] = {0.f, 0.f, 0.f, 0.f};
     const int t0 = __ldg(a.hub.hub_task_ptr + hub), t1 = __ldg(a.hub.hub_task_ptr + hub + 1);
-    for (int t = t0; t < t1; ++t) {
-        const float* part = a.hub.partial + (long)t * a.hub.ldpart;
+    cta_sum_partials<1>(a.hub.partial, a.hub.ldpart, t0, t1, 2 * SPK_MAX_HEADS, &red[0][0], 2 * SPK_MAX_HEADS);
+    if (wid != 0) return;
+    RowCtx<NCH, HT> rc;
+    bwd_row_prologue<NCH, HT>(a, row, lane, rc);
+    float usum[HT], swsum[HT];
 #pragma unroll
-        for (int h = 0; h < SPK_MAX_HEADS; ++h) { usum[h] += part[h]; swsum[h] += part[SPK_MAX_HEADS + h]; }
-    }
-    bwd_row_store<NCH>(a, row, lane, rc, usum, swsum, true, true);
+    for (int h = 0; h < HT; ++h) { usum[h] = red[0][h]; swsum[h] = red[0][SPK_MAX_HEADS + h]; }
+    bwd_row_store<NCH, HT>(a, row, lane, rc, usum, swsum, true, true);
 }
 
-template <int NCH, bool HAS2>
+template <int NCH, int HT, bool HAS2>
 static int launch_bwd_rows_t(const EdgeBwdRowsArgs& a, cudaStream_t s) {
     if (a.n_rows > 0) {
         const unsigned grid = (a.n_rows + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        edge_bwd_rows_kernel<NCH, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        edge_bwd_rows_kernel<NCH, HT, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("edge_bwd_rows")) return rc;
     }
     if (a.hub.n_tasks > 0) {
         const unsigned grid = (a.hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        edge_bwd_rows_tasks_kernel<NCH, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        edge_bwd_rows_tasks_kernel<NCH, HT, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("edge_bwd_rows_tasks")) return rc;
-        const unsigned gridh = (a.hub.n_hubs + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        edge_bwd_rows_hub_finalize_kernel<NCH><<<gridh, SPK_CTA_THREADS, 0, s>>>(a);
+        edge_bwd_rows_hub_finalize_kernel<NCH, HT><<<a.hub.n_hubs, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("edge_bwd_rows_hub_finalize")) return rc;
     }
     return 0;
 }
 
-int launch_edge_bwd_rows(const EdgeBwdRowsArgs& a, cudaStream_t s) {
-    const int nch = (a.g.Wd4 + 31) / 32;
+template <int NCH>
+static int launch_bwd_rows_n(const EdgeBwdRowsArgs& a, cudaStream_t s) {
     const bool has2 = a.t2 != nullptr;
-#define SPK_CASE(N) case N: return has2 ? launch_bwd_rows_t<N, true>(a, s) : launch_bwd_rows_t<N, false>(a, s);
-    switch (nch) {
-        SPK_CASE(1) SPK_CASE(2) SPK_CASE(3) SPK_CASE(4)
+    if (a.g.H == 1) return has2 ? launch_bwd_rows_t<NCH, 1, true>(a, s) : launch_bwd_rows_t<NCH, 1, false>(a, s);
+    if (a.g.H == 2) return has2 ? launch_bwd_rows_t<NCH, 2, true>(a, s) : launch_bwd_rows_t<NCH, 2, false>(a, s);
+    return has2 ? launch_bwd_rows_t<NCH, 4, true>(a, s) : launch_bwd_rows_t<NCH, 4, false>(a, s);
+}
+
+int launch_edge_bwd_rows(const EdgeBwdRowsArgs& a, cudaStream_t s) {
+    switch ((a.g.Wd4 + 31) / 32) {
+        case 1: return launch_bwd_rows_n<1>(a, s);
+        case 2: return launch_bwd_rows_n<2>(a, s);
+        case 3: return launch_bwd_rows_n<3>(a, s);
+        case 4: return launch_bwd_rows_n<4>(a, s);
         default: set_error("edge_bwd_rows: row width %d floats exceeds the supported 512", a.g.Wd4 * 4); return 2;
     }
-#undef SPK_CASE
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,25 +423,19 @@ seg_gather_tasks_kernel(const SegGatherArgs a) {
 template <int NCH>
 __global__ void __launch_bounds__(SPK_CTA_THREADS)
 seg_gather_hub_finalize_kernel(const SegGatherArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int hub = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (hub >= a.hub.n_hubs) return;
+    __shared__ __align__(16) float red[SPK_WARPS_PER_CTA][NCH * 128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int hub = blockIdx.x;
     const int seg = __ldg(a.hub.hub_seg + hub);
-    int hc[NCH];
-    SegAcc<NCH> st;
-    seg_init<NCH>(a.g, lane, hc, st);
     const int t0 = __ldg(a.hub.hub_task_ptr + hub), t1 = __ldg(a.hub.hub_task_ptr + hub + 1);
-    for (int t = t0; t < t1; ++t) {
-        const float* part = a.hub.partial + (long)t * a.hub.ldpart;
+    cta_sum_partials<NCH * 4>(a.hub.partial, a.hub.ldpart, t0, t1, a.g.Wd4 * 4, &red[0][0], NCH * 128);
+    if (wid != 0) return;
+    float* dst = a.outp + (long)seg * a.ldout;             // partial rows already have the output format
 #pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-            const int c4 = lane + 32 * ci;
-            if (c4 < a.g.Dt4) st.acc[ci] = f4add(st.acc[ci], *reinterpret_cast<const float4*>(part + c4 * 4));
-        }
-#pragma unroll
-        for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] += part[a.g.Dt4 * 4 + h];
+    for (int ci = 0; ci < NCH; ++ci) {
+        const int c4 = lane + 32 * ci;
+        if (c4 < a.g.Wd4) *reinterpret_cast<float4*>(dst + c4 * 4) = *reinterpret_cast<const float4*>(&red[0][c4 * 4]);
     }
-    seg_store<NCH>(a.outp + (long)seg * a.ldout, a.g, lane, st);
 }
 
 template <int NCH>
@@ -439,8 +449,7 @@ static int launch_seg_t(const SegGatherArgs& a, cudaStream_t s) {
         const unsigned grid = (a.hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
         seg_gather_tasks_kernel<NCH><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("seg_gather_tasks")) return rc;
-        const unsigned gridh = (a.hub.n_hubs + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        seg_gather_hub_finalize_kernel<NCH><<<gridh, SPK_CTA_THREADS, 0, s>>>(a);
+        seg_gather_hub_finalize_kernel<NCH><<<a.hub.n_hubs, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("seg_gather_hub_finalize")) return rc;
     }
     return 0;

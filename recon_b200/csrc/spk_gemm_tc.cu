@@ -1,0 +1,342 @@
+// K1 / K5 on the 5th-generation tensor cores: fp32-accurate GEMM by 3xTF32 error compensation.
+//
+//   C[M,N] (+)= A[M,K] * B[K,N],   A = A_hi + A_lo,  B = B_hi + B_lo  (hi = top 19 bits, lo = remainder)
+//   C ~= A_hi*B_hi + A_lo*B_hi + A_hi*B_lo        (fp32 accumulation in TMEM; dropped term ~2^-20)
+//
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A (raw fp32) and of the pre-split, pre-transposed
+//               weights B_hi / B_lo ([N,K], K-major) into a 128B-swizzled shared-memory ring
+//   warps 2-5   splitter: rewrite the raw A tile in place as A_hi and write A_lo beside it
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) x3 per K-step,
+//               accumulators in TMEM (two 256-column buffers, ping-pong across tiles)
+//   warps 6-9   epilogue: tcgen05.ld accumulator rows -> registers -> global (optional C += )
+// mbarriers: full (TMA->splitter/MMA), conv (splitter->MMA), empty (MMA commit->TMA),
+//            tfull (MMA commit->epilogue), tempty (epilogue->MMA).
+// The projection GEMMs this serves are the re-associated `a.mm(edge_h)` of GAT/layers.py:137
+//  and its autograd products; weights are tiny so B is split once per call on the device.
+#include <cuda.h>
+#include "spk_common.cuh"
+#include "spk_gemm.cuh"
+
+namespace spk {
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                       // 32 fp32 = 128 B = one swizzle row
+constexpr int TC_A_TILE = TC_BM * TC_BK * 4;    // 16 KB
+constexpr int TC_THREADS = 320;
+constexpr int TC_MAX_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (1u << 16);          // start address | LBO (unused with swizzle)
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);        // SBO | descriptor version 1 | SWIZZLE_128B
+    return ((uint64_t)hi << 32) | lo;
+}
+
+struct TcParams {
+    float* C; long ldc; long M; int N; int K; int BN; int n_tiles_n; int stages; int accumulate; int c_vec;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                  const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 4];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_tile = (uint32_t)p.BN * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_TILE + 2u * b_tile;
+    auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
+    auto a_lo = [&](int s) { return base + (uint32_t)s * stage_bytes + TC_A_TILE; };
+    auto b_hi = [&](int s) { return base + (uint32_t)s * stage_bytes + 2u * TC_A_TILE; };
+    auto b_lo = [&](int s) { return base + (uint32_t)s * stage_bytes + 2u * TC_A_TILE + b_tile; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto conv = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * TC_MAX_STAGES + s); };
+    auto tfull = [&](int a) { return bar0 + 8u * (3 * TC_MAX_STAGES + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (3 * TC_MAX_STAGES + 2 + a); };
+
+    const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    const long m_tiles = (p.M + TC_BM - 1) / TC_BM;
+    const long total = m_tiles * p.n_tiles_n;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                           // ---- TMA producer
+            uint32_t it = 0;
+            for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m0 = (int)(tile / p.n_tiles_n) * TC_BM, n0 = (int)(tile % p.n_tiles_n) * p.BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full(s), TC_A_TILE + 2u * b_tile);
+                    tma_load_2d(a_hi(s), &tmA, full(s), kb * TC_BK, m0);
+                    tma_load_2d(b_hi(s), &tmBhi, full(s), kb * TC_BK, n0);
+                    tma_load_2d(b_lo(s), &tmBlo, full(s), kb * TC_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                           // ---- MMA issuer
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            uint32_t it = 0, tl = 0;
+            for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+                const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+                mbar_wait(tempty(acc), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(full(s), ph);
+                    mbar_wait(conv(s), ph);
+                    tc_fence_after();
+                    const uint64_t dah = make_kmajor_sw128_desc(a_hi(s)), dal = make_kmajor_sw128_desc(a_lo(s));
+                    const uint64_t dbh = make_kmajor_sw128_desc(b_hi(s)), dbl = make_kmajor_sw128_desc(b_lo(s));
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        if (kb * TC_BK + ks * 8 >= p.K) break;
+                        const uint64_t o = (uint64_t)(2 * ks);      // 32 B per K-step, in 16-byte units
+                        tc_mma_tf32(d_tmem, dal + o, dbh + o, idesc, (kb | ks) != 0);
+                        tc_mma_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
+                        tc_mma_tf32(d_tmem, dah + o, dbh + o, idesc, 1u);
+                    }
+                    tc_commit(empty(s));                            // frees the smem stage when these MMAs retire
+                }
+                tc_commit(tfull(acc));                              // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp < 6) {                                         // ---- splitter: raw fp32 -> (hi, lo)
+        const int t = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1u;
+                mbar_wait(full(s), ph);
+                const uint32_t hi0 = a_hi(s), lo0 = a_lo(s);
+#pragma unroll
+                for (int i = 0; i < TC_A_TILE / 16 / 128; ++i) {
+                    const uint32_t off = (uint32_t)(t + 128 * i) * 16u;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi0 + off));
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi0 + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA's async proxy
+                mbar_arrive(conv(s));
+            }
+        }
+    } else {                                                       // ---- epilogue (warps 6..9)
+        const int q = warp & 3;                                    // TMEM lane quarter this warp may access
+        uint32_t tl = 0;
+        for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+            const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+            const long row = (tile / p.n_tiles_n) * TC_BM + q * 32 + lane;
+            const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
+            mbar_wait(tfull(acc), aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < p.BN; c0 += 16) {
+                uint32_t r[16];
+                const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (row < p.M) {
+                    float* crow = p.C + row * p.ldc;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const int col = n0 + c0 + j;
+                        if (col >= p.N) break;
+                        float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        if (p.c_vec && col + 3 < p.N) {
+                            if (p.accumulate) o = f4add(o, *reinterpret_cast<const float4*>(crow + col));
+                            *reinterpret_cast<float4*>(crow + col) = o;
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (col + k < p.N) crow[col + k] = p.accumulate ? crow[col + k] + ov[k] : ov[k];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Bt_hi/Bt_lo[n, k] = split(B[k, n]) : transposed (K-major), zero padded to ldt
+__global__ void tc_prepare_b_kernel(const float* __restrict__ B, long ldb, int K, int N, float* __restrict__ hi,
+                                    float* __restrict__ lo, int ldt) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)N * ldt) return;
+    const int n = (int)(i / ldt), k = (int)(i % ldt);
+    const float x = k < K ? B[(long)k * ldb + n] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = x - h;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = [box_rows, 32 cols], 128B swizzle, OOB -> 0
+int make_map(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return 3; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return 3; }
+    return 0;
+}
+}  // namespace
+
+int gemm_tc_ldt(int K) { return (K + 3) / 4 * 4; }
+
+int gemm_nn_tc_supported(const float* A, long lda, long M, int N, int K) {
+    return M >= 1 && N >= 1 && K >= 1 && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && lda >= K;
+}
+
+// workspace: 2 * N * ldt floats for the split / transposed weights
+int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N, int K,
+               int accumulate, float* workspace, cudaStream_t s) {
+    const int ldt = gemm_tc_ldt(K);
+    float* bhi = workspace;
+    float* blo = workspace + (long)N * ldt;
+    const long nb = (long)N * ldt;
+    tc_prepare_b_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, s>>>(B, ldb, K, N, bhi, blo, ldt);
+    if (int rc = check_launch("tc_prepare_b")) return rc;
+
+    const int n_tiles_n = (N + 255) / 256;
+    int BN = ((N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
+    if (BN < 16) BN = 16;
+    const int b_tile = BN * 128;
+    const int stage_bytes = 2 * TC_A_TILE + 2 * b_tile;
+    int stages = (225 * 1024 - 1024) / stage_bytes;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    if (stages < 1) { set_error("gemm_tc: tile does not fit shared memory"); return 3; }
+    const int smem = stages * stage_bytes + 1024;
+
+    CUtensorMap tmA, tmBhi, tmBlo;
+    if (int rc = make_map(&tmA, A, M, K, lda, TC_BM)) return rc;
+    if (int rc = make_map(&tmBhi, bhi, N, K, ldt, BN)) return rc;
+    if (int rc = make_map(&tmBlo, blo, N, K, ldt, BN)) return rc;
+
+    TcParams p;
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.n_tiles_n = n_tiles_n; p.stages = stages;
+    p.accumulate = accumulate;
+    p.c_vec = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    static int smem_set = 0;
+    if (smem_set < smem) {
+        if (cudaFuncSetAttribute(gemm_nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+            set_error("gemm_tc: cannot raise dynamic shared memory limit");
+            (void)cudaGetLastError();
+            return 3;
+        }
+        smem_set = 226 * 1024;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long total = ((M + TC_BM - 1) / TC_BM) * n_tiles_n;
+    const unsigned grid = (unsigned)(total < sms ? total : sms);
+    gemm_nn_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmBhi, tmBlo, p);
+    return check_launch("gemm_nn_tc");
+}
+
+}  // namespace spk

@@ -18,6 +18,8 @@ from . import _lib
 from .graph import KGraph
 
 MAX_HEADS = 4
+USE_TC = True          # route eligible products through the tcgen05 3xTF32 GEMM (else the exact-fp32 SIMT GEMM)
+TC_MIN_ROWS = 1        # (tests lower/raise this to exercise both paths)
 
 
 class Geometry:
@@ -73,8 +75,16 @@ def gemm_nn(A, B, out=None, accumulate=False):
             if not accumulate:
                 out.zero_()
             return out
-        _lib.check(_lib.load().spk_gemm_nn(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
-                                           out.stride(0), M, N, K, int(accumulate), _lib.stream_ptr()), "gemm_nn")
+        lib = _lib.load()
+        if USE_TC and M >= TC_MIN_ROWS and N <= 512 and lib.spk_gemm_nn_tc_supported(_lib.ptr(A), A.stride(0), M, N, K):
+            # tcgen05 tensor cores, 3xTF32 (fp32-accurate)
+            ws = torch.empty(lib.spk_gemm_tc_workspace_floats(N, K), dtype=torch.float32, device=A.device)
+            _lib.check(lib.spk_gemm_nn_tc(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
+                                          out.stride(0), M, N, K, int(accumulate), _lib.ptr(ws), _lib.stream_ptr()),
+                       "gemm_nn_tc")
+        else:
+            _lib.check(lib.spk_gemm_nn(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
+                                       out.stride(0), M, N, K, int(accumulate), _lib.stream_ptr()), "gemm_nn")
     return out
 
 
@@ -95,12 +105,22 @@ def gemm_tn(A, B, out=None, accumulate=False):
     return out
 
 
+def tc_friendly(X):
+    """Row stride multiple of 4 floats (16 B) so TMA can fetch the operand; pads a copy when needed."""
+    if X.dim() != 2 or X.stride(1) != 1 or X.stride(0) % 4 == 0 or not USE_TC:
+        return X
+    f = X.shape[1]
+    Xp = X.new_zeros(X.shape[0], (f + 3) // 4 * 4)
+    Xp[:, :f] = X
+    return Xp[:, :f]
+
+
 class MatMulFn(torch.autograd.Function):
     """X @ W with the library GEMMs (relation_embed.mm(W) models.py:77, entity_embeddings.mm(W_entities) 175)."""
 
     @staticmethod
     def forward(ctx, X, W):
-        X = X.contiguous(); W = W.contiguous()
+        X = tc_friendly(X.contiguous()); W = W.contiguous()
         ctx.save_for_backward(X, W)
         return gemm_nn(X, W)
 
@@ -203,7 +223,7 @@ class AttentionGroupFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, X, Wn, Rel, Wr, graph, geom, alpha, apply_elu, mask_csr, nanflag):
-        X = X.contiguous(); Wn = Wn.contiguous(); Rel = Rel.contiguous(); Wr = Wr.contiguous()
+        X = tc_friendly(X.contiguous()); Wn = Wn.contiguous(); Rel = Rel.contiguous(); Wr = Wr.contiguous()
         P = gemm_nn(X, Wn)                      # [N, 2Wd] = [P1~ | P2~]
         P3 = gemm_nn(Rel, Wr)                   # [R, Wd]
         out, den, sw = edge_attn_forward(graph, P[:, :geom.Wd], P[:, geom.Wd:], P3, geom, alpha, apply_elu,

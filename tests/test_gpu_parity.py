@@ -102,26 +102,48 @@ def test_kgraph_empty():
 
 
 # ---- K1/K5: GEMMs ---------------------------------------------------------------------------------
-@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (130, 50, 416), (1000, 200, 416), (257, 416, 50), (3, 7, 5), (4096, 64, 200)])
-def test_gemm_nn(m, k, n):
+@pytest.fixture(params=["tc", "simt"])
+def gemm_path(request):
+    """Run the test once on the tcgen05 3xTF32 GEMM and once on the exact-fp32 SIMT GEMM."""
+    from recon_b200 import functional as SF
+    old = SF.USE_TC
+    SF.USE_TC = request.param == "tc"
+    yield request.param
+    SF.USE_TC = old
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (130, 50, 416), (1000, 200, 416), (257, 416, 50), (3, 7, 5), (4096, 64, 200),
+                                   (20000, 52, 416), (70001, 200, 208), (5000, 416, 200), (9999, 12, 24)])
+def test_gemm_nn(m, k, n, gemm_path):
     from recon_b200.functional import gemm_nn
     g = torch.Generator().manual_seed(m + k + n)
     a = torch.randn(m, k, generator=g); b = torch.randn(k, n, generator=g)
+    tol = 2e-6 if gemm_path == "simt" else 1e-5      # 3xTF32: dropped lo*lo term + tensor-core accumulation
     c = gemm_nn(a.to(dev()), b.to(dev()))
-    assert rel_l2(c, a.double() @ b.double()) < 2e-6
+    assert rel_l2(c, a.double() @ b.double()) < tol
     c0 = torch.randn(m, n, generator=g)
     c2 = gemm_nn(a.to(dev()), b.to(dev()), out=c0.to(dev()), accumulate=True)
-    assert rel_l2(c2, c0.double() + a.double() @ b.double()) < 2e-6
+    assert rel_l2(c2, c0.double() + a.double() @ b.double()) < tol
 
 
-def test_gemm_nn_strided_views():
+def test_gemm_nn_tc_wide_dynamic_range():
+    """3xTF32 must stay fp32-accurate when magnitudes vary over many binades."""
+    from recon_b200.functional import gemm_nn
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(3000, 200, generator=g) * torch.exp(4 * torch.randn(3000, 200, generator=g))
+    b = torch.randn(200, 416, generator=g) * torch.exp(4 * torch.randn(200, 416, generator=g))
+    c = gemm_nn(a.to(dev()), b.to(dev()))
+    assert rel_l2(c, a.double() @ b.double()) < 1e-5
+
+
+def test_gemm_nn_strided_views(gemm_path):
     from recon_b200.functional import gemm_nn
     g = torch.Generator().manual_seed(0)
     big = torch.randn(300, 96, generator=g).to(dev()); b = torch.randn(40, 24, generator=g).to(dev())
     a = big[:, 8:48]
     out = torch.zeros(300, 64, device=dev())
     gemm_nn(a, b, out=out[:, 16:40])
-    assert rel_l2(out[:, 16:40], a.double().cpu() @ b.double().cpu()) < 2e-6
+    assert rel_l2(out[:, 16:40], a.double().cpu() @ b.double().cpu()) < 1e-5
     assert float(out[:, :16].abs().sum()) == 0.0 and float(out[:, 40:].abs().sum()) == 0.0
 
 
@@ -310,4 +332,6 @@ def test_training_mode_dropout_runs_and_is_unbiased_in_shape():
     model.eval()
     a = model(None, torch.arange(n), (edge, etype), nhop)[0]
     b = model(None, torch.arange(n), (edge, etype), nhop)[0]
-    assert torch.equal(a, b)
+    # eval mode: no dropout. (Not bit-equal: every forward re-normalises entity_embeddings.data in place,
+    # models.py:160-161, and normalize(normalize(x)) differs from normalize(x) in the last ulp.)
+    assert torch.allclose(a, b, atol=1e-6)
