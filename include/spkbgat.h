@@ -83,6 +83,13 @@ int64_t spk_gemm_tc_workspace_floats(int32_t N, int32_t K);
 int spk_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                    int64_t M, int32_t N, int32_t K, int32_t accumulate, float* workspace, spk_stream_t stream);
 
+/* C[Ka,Nb] (+)= A[M,Ka]^T * B[M,Nb] on tcgen05 (MN-major operands, both split hi/lo in shared memory),
+ * one CTA per (tile, m-split), partials added in split order. */
+int32_t spk_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb);
+int64_t spk_gemm_tn_tc_workspace_floats(int64_t M, int32_t Ka, int32_t Nb);
+int spk_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int32_t Ka, int32_t Nb, int32_t accumulate, float* workspace, spk_stream_t stream);
+
 /* ---- K2: fused attention forward (replaces SpGraphAttentionLayer.forward layers.py:124-175 for all
  *      heads of a group, incl. both SpecialSpmmFinal calls, the divide and the ELU) ---- */
 typedef struct {

@@ -79,6 +79,9 @@ SIGNATURES = {
     "spk_gemm_nn_tc_supported": (_I32, [_VP, _I64, _I64, _I32, _I32]),
     "spk_gemm_tc_workspace_floats": (_I64, [_I32, _I32]),
     "spk_gemm_nn_tc": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
+    "spk_gemm_tn_tc_supported": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _I32]),
+    "spk_gemm_tn_tc_workspace_floats": (_I64, [_I64, _I32, _I32]),
+    "spk_gemm_tn_tc": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
     "spk_gemm_tn_workspace_floats": (_I64, [_I64, _I32, _I32]),
     "spk_gemm_tn": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
     "spk_edge_attn_fwd": (_I32, [C.POINTER(EdgeFwdArgs), _VP]),

@@ -142,6 +142,18 @@ int spk_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, flo
     return gemm_nn_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, workspace, (cudaStream_t)stream);
 }
 
+int32_t spk_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb) {
+    return gemm_tn_tc_supported(A, lda, B, ldb, M, Ka, Nb);
+}
+int64_t spk_gemm_tn_tc_workspace_floats(int64_t M, int32_t Ka, int32_t Nb) { return gemm_tn_tc_workspace_floats(M, Ka, Nb); }
+int spk_gemm_tn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t M, int32_t Ka, int32_t Nb, int32_t accumulate, float* workspace, spk_stream_t stream) {
+    if (ldc < Nb) { set_error("gemm_tn_tc: leading dimension too small"); return 1; }
+    if (!gemm_tn_tc_supported(A, lda, B, ldb, M, Ka, Nb)) { set_error("gemm_tn_tc: operands must be 16-byte aligned with ld %% 4 == 0"); return 1; }
+    if (!workspace) { set_error("gemm_tn_tc: workspace required"); return 1; }
+    return gemm_tn_tc(A, lda, B, ldb, C, ldc, M, Ka, Nb, accumulate, workspace, (cudaStream_t)stream);
+}
+
 int spk_edge_attn_fwd(const spk_edge_fwd_args* p, spk_stream_t stream) {
     EdgeFwdArgs a;
     if (!geom_ok(p->geom, &a.g, "edge_attn_fwd")) return 1;

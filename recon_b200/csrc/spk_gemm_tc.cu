@@ -271,7 +271,8 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor [rows, cols] with row stride ld (floats); box = [box_rows, 32 cols], 128B swizzle, OOB -> 0
-int make_map(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld, int box_rows) {
+int make_map(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld, int box_rows,
+             CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return 3; }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -279,7 +280,7 @@ int make_map(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld, i
     cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return 3; }
     return 0;
@@ -337,6 +338,258 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     const unsigned grid = (unsigned)(total < sms ? total : sms);
     gemm_nn_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmBhi, tmBlo, p);
     return check_launch("gemm_nn_tc");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// TN product on the tensor cores:  D[Ka, Nb] = sum_m X[m, Ka] * G[m, Nb]   (weight gradients, K5)
+// Both operands are activations stored with the reduction index m as the ROW index, i.e. "MN-major"
+// for the MMA: TMA lands [32 m-rows x 32 columns] boxes (128B swizzle with 32B atomicity, the only
+// MN-major layout the tensor core takes for 32-bit operands); the UMMA descriptors use the MN-major
+// canonical layout (LBO = distance between 32-column chunks, SBO = distance between 4-row groups)
+// and the instruction descriptor sets a_major = b_major = MN. Both tiles are split hi/lo in
+// shared memory by the splitter warps. One CTA = one (Ka-tile, Nb-tile, m-split); the per-split
+// partials are added in split order by tn_reduce (deterministic).
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int TN_BKM = 32;                     // m rows per pipeline stage (4 MMA K-steps)
+constexpr int TN_CHUNK = TN_BKM * 128;         // one [32 rows x 32 cols] box = 4 KB
+constexpr int TN_ACH = 4;                      // A chunks: 4 x 32 = 128 = UMMA M
+
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
+    // 32-bit MN-major operands must use the 128B swizzle with 32B atomicity (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B,
+    // Swizzle<2,5,2>): rows of 128 B, swizzle period 4 rows, canonical layout ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) floats.
+    const uint32_t lo = ((saddr >> 4) & 0x3fffu) | ((uint32_t)(TN_CHUNK >> 4) << 16);   // start | LBO: next 32-col chunk
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);                         // SBO: next 4-row group | v1 | SW128_BASE32B
+    return ((uint64_t)hi << 32) | lo;
+}
+
+struct TnParams {
+    float* part; long M; int Ka; int Nb; int BN; int n_tiles_n; int n_tiles_k; int splits; long m_per_split; int stages;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const TnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int nbc = p.BN / 32;                                     // B chunks
+    const uint32_t half = (uint32_t)(TN_ACH + nbc) * TN_CHUNK;     // raw/hi part of a stage; lo part follows
+    const uint32_t stage_bytes = 2u * half;
+    auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
+    auto b_hi = [&](int s) { return base + (uint32_t)s * stage_bytes + TN_ACH * TN_CHUNK; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto conv = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * TC_MAX_STAGES + s); };
+    const uint32_t tfull = bar0 + 8u * (3 * TC_MAX_STAGES);
+
+    const int tile = blockIdx.x % (p.n_tiles_k * p.n_tiles_n);
+    const int split = blockIdx.x / (p.n_tiles_k * p.n_tiles_n);
+    const int ka0 = (tile / p.n_tiles_n) * 128, nb0 = (tile % p.n_tiles_n) * p.BN;
+    const long mbeg = (long)split * p.m_per_split;
+    long mend = mbeg + p.m_per_split;
+    if (mend > p.M) mend = p.M;
+    const int num_kb = mend > mbeg ? (int)((mend - mbeg + TN_BKM - 1) / TN_BKM) : 0;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                           // ---- TMA producer
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1u;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full(s), half);
+                // rows beyond `mend` belong to the next split: clamp by loading them and zeroing in the splitter
+                const int m0 = (int)(mbeg + (long)kb * TN_BKM);
+                for (int c = 0; c < TN_ACH; ++c) tma_load_2d(a_hi(s) + c * TN_CHUNK, &tmX, full(s), ka0 + 32 * c, m0);
+                for (int c = 0; c < nbc; ++c) tma_load_2d(b_hi(s) + c * TN_CHUNK, &tmG, full(s), nb0 + 32 * c, m0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                           // ---- MMA issuer
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1u;
+                mbar_wait(full(s), ph);
+                mbar_wait(conv(s), ph);
+                tc_fence_after();
+                const uint64_t dah = make_mnmajor_sw128_desc(a_hi(s)), dal = make_mnmajor_sw128_desc(a_hi(s) + half);
+                const uint64_t dbh = make_mnmajor_sw128_desc(b_hi(s)), dbl = make_mnmajor_sw128_desc(b_hi(s) + half);
+#pragma unroll
+                for (int ks = 0; ks < TN_BKM / 8; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * (1024 >> 4));     // next 8-row group
+                    tc_mma_tf32(tmem_base, dal + o, dbh + o, idesc, (kb | ks) != 0);
+                    tc_mma_tf32(tmem_base, dah + o, dbl + o, idesc, 1u);
+                    tc_mma_tf32(tmem_base, dah + o, dbh + o, idesc, 1u);
+                }
+                tc_commit(empty(s));
+            }
+            tc_commit(tfull);
+        }
+    } else if (warp < 6) {                                         // ---- splitter: both tiles, raw -> (hi, lo)
+        const int t = threadIdx.x - 64;
+        const int n16 = (int)(half / 16);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (kb / p.stages) & 1u;
+            mbar_wait(full(s), ph);
+            const uint32_t hi0 = a_hi(s), lo0 = a_hi(s) + half;
+            const long m0 = mbeg + (long)kb * TN_BKM;
+            const int valid_rows = (int)(mend - m0 < TN_BKM ? mend - m0 : TN_BKM);   // rows past the split end count as 0
+            for (int i = t; i < n16; i += 128) {
+                const uint32_t off = (uint32_t)i * 16u;
+                const int r = (i >> 3) & (TN_BKM - 1);             // row inside the 4 KB chunk (128 B per row)
+                float4 x;
+                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi0 + off));
+                if (r >= valid_rows) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi0 + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(conv(s));
+        }
+    } else {                                                       // ---- epilogue: TMEM -> partial[split][ka][nb]
+        const int q = warp & 3;
+        const int ka = ka0 + q * 32 + lane;
+        float* prow = p.part + ((long)split * p.Ka + ka) * p.Nb;
+        if (num_kb > 0) {
+            mbar_wait(tfull, 0);
+            tc_fence_after();
+        }
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            uint32_t r[16];
+            if (num_kb > 0) {
+                const uint32_t taddr = tmem_base + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            if (ka < p.Ka) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int nb = nb0 + c0 + j;
+                    if (nb < p.Nb) prow[nb] = __uint_as_float(r[j]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// 2-D fp32 tensor [rows, cols], box = [32 rows x 32 cols], 128B swizzle
+int make_map_tn(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld) {
+    return make_map(tm, ptr, rows, cols, ld, TN_BKM, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+}
+
+__global__ void tn_reduce_tc_kernel(const float* __restrict__ part, int splits, long elems, int Nb,
+                                    float* __restrict__ C, long ldc, int accumulate) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= elems) return;
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(long)z * elems + idx];     // fixed order
+    float* c = C + (idx / Nb) * ldc + (idx % Nb);
+    *c = accumulate ? *c + s : s;
+}
+
+struct TnPlan { int n_tiles_k, n_tiles_n, BN, splits, stages, smem; long m_per_split; };
+
+TnPlan tn_plan(long M, int Ka, int Nb) {
+    TnPlan pl;
+    pl.n_tiles_k = (Ka + 127) / 128;
+    pl.n_tiles_n = (Nb + 255) / 256;
+    pl.BN = ((Nb + pl.n_tiles_n - 1) / pl.n_tiles_n + 31) / 32 * 32;
+    const int tiles = pl.n_tiles_k * pl.n_tiles_n;
+    long splits = (148 + tiles - 1) / tiles;
+    const long max_by_m = (M + 1023) / 1024;
+    if (splits > max_by_m) splits = max_by_m;
+    if (splits < 1) splits = 1;
+    long mps = (M + splits - 1) / splits;
+    mps = (mps + TN_BKM - 1) / TN_BKM * TN_BKM;
+    if (mps < TN_BKM) mps = TN_BKM;
+    pl.splits = (int)((M + mps - 1) / mps);
+    if (pl.splits < 1) pl.splits = 1;
+    pl.m_per_split = mps;
+    const int stage_bytes = 2 * (TN_ACH + pl.BN / 32) * TN_CHUNK;
+    pl.stages = (225 * 1024 - 1024) / stage_bytes;
+    if (pl.stages > TC_MAX_STAGES) pl.stages = TC_MAX_STAGES;
+    pl.smem = pl.stages * stage_bytes + 1024;
+    return pl;
+}
+}  // namespace
+
+int gemm_tn_tc_supported(const float* A, long lda, const float* B, long ldb, long M, int Ka, int Nb) {
+    return M >= 1 && Ka >= 1 && Nb >= 1 && (lda % 4 == 0) && (ldb % 4 == 0) && lda >= Ka && ldb >= Nb &&
+           ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+}
+
+long gemm_tn_tc_workspace_floats(long M, int Ka, int Nb) {
+    const TnPlan pl = tn_plan(M, Ka, Nb);
+    return (long)pl.splits * Ka * Nb;
+}
+
+int gemm_tn_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int Ka, int Nb,
+               int accumulate, float* workspace, cudaStream_t s) {
+    const TnPlan pl = tn_plan(M, Ka, Nb);
+    CUtensorMap tmX, tmG;
+    if (int rc = make_map_tn(&tmX, A, M, Ka, lda)) return rc;
+    if (int rc = make_map_tn(&tmG, B, M, Nb, ldb)) return rc;
+    TnParams p;
+    p.part = workspace; p.M = M; p.Ka = Ka; p.Nb = Nb; p.BN = pl.BN; p.n_tiles_n = pl.n_tiles_n; p.n_tiles_k = pl.n_tiles_k;
+    p.splits = pl.splits; p.m_per_split = pl.m_per_split; p.stages = pl.stages;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
+            set_error("gemm_tn_tc: cannot raise dynamic shared memory limit");
+            (void)cudaGetLastError();
+            return 3;
+        }
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)(pl.n_tiles_k * pl.n_tiles_n * pl.splits);
+    gemm_tn_tc_kernel<<<grid, TC_THREADS, pl.smem, s>>>(tmX, tmG, p);
+    if (int rc = check_launch("gemm_tn_tc")) return rc;
+    const long elems = (long)Ka * Nb;
+    tn_reduce_tc_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, s>>>(workspace, pl.splits, elems, Nb, C, ldc, accumulate);
+    return check_launch("tn_reduce_tc");
 }
 
 }  // namespace spk

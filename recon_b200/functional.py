@@ -99,9 +99,16 @@ def gemm_tn(A, B, out=None, accumulate=False):
         assert not accumulate
         out = torch.empty(Ka, Nb, dtype=torch.float32, device=A.device)
     if Ka and Nb:
-        ws = torch.empty(max(1, lib.spk_gemm_tn_workspace_floats(M, Ka, Nb)), dtype=torch.float32, device=A.device)
-        _lib.check(lib.spk_gemm_tn(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out), out.stride(0),
-                                   M, Ka, Nb, int(accumulate), _lib.ptr(ws), _lib.stream_ptr()), "gemm_tn")
+        if USE_TC and M >= TC_MIN_ROWS and lib.spk_gemm_tn_tc_supported(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0),
+                                                                        M, Ka, Nb):
+            ws = torch.empty(max(1, lib.spk_gemm_tn_tc_workspace_floats(M, Ka, Nb)), dtype=torch.float32, device=A.device)
+            _lib.check(lib.spk_gemm_tn_tc(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
+                                          out.stride(0), M, Ka, Nb, int(accumulate), _lib.ptr(ws), _lib.stream_ptr()),
+                       "gemm_tn_tc")
+        else:
+            ws = torch.empty(max(1, lib.spk_gemm_tn_workspace_floats(M, Ka, Nb)), dtype=torch.float32, device=A.device)
+            _lib.check(lib.spk_gemm_tn(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out), out.stride(0),
+                                       M, Ka, Nb, int(accumulate), _lib.ptr(ws), _lib.stream_ptr()), "gemm_tn")
     return out
 
 

@@ -147,15 +147,30 @@ def test_gemm_nn_strided_views(gemm_path):
     assert float(out[:, :16].abs().sum()) == 0.0 and float(out[:, 40:].abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("m,ka,nb", [(1, 1, 1), (5000, 50, 416), (70000, 200, 416), (333, 7, 5), (100000, 11, 208)])
-def test_gemm_tn_deterministic(m, ka, nb):
+@pytest.mark.parametrize("m,ka,nb", [(1, 1, 1), (5000, 52, 416), (70000, 200, 416), (333, 8, 4), (100000, 12, 208),
+                                     (40, 200, 416), (33000, 416, 200), (1025, 300, 24), (333, 7, 5)])
+def test_gemm_tn_deterministic(m, ka, nb, gemm_path):
     from recon_b200.functional import gemm_tn
     g = torch.Generator().manual_seed(m)
     a = torch.randn(m, ka, generator=g); b = torch.randn(m, nb, generator=g)
     c = gemm_tn(a.to(dev()), b.to(dev()))
-    assert rel_l2(c, a.double().t() @ b.double()) < 5e-6
+    assert rel_l2(c, a.double().t() @ b.double()) < (5e-6 if gemm_path == "simt" else 2e-5)
     c2 = gemm_tn(a.to(dev()), b.to(dev()))
     assert torch.equal(c, c2)
+    c0 = torch.randn(ka, nb, generator=g)
+    c3 = gemm_tn(a.to(dev()), b.to(dev()), out=c0.to(dev()), accumulate=True)
+    assert rel_l2(c3, c0.double() + a.double().t() @ b.double()) < 2e-5
+
+
+def test_gemm_tn_tc_padded_view():
+    """X given as a [:, :50] view of a 52-wide buffer (what tc_friendly produces for 50-dim embeddings)."""
+    from recon_b200.functional import gemm_tn
+    g = torch.Generator().manual_seed(1)
+    xp = torch.randn(9000, 52, generator=g).to(dev()); gp = torch.randn(9000, 416, generator=g).to(dev())
+    x = xp[:, :50]
+    c = gemm_tn(x, gp)
+    assert c.shape == (50, 416)
+    assert rel_l2(c, x.double().cpu().t() @ gp.double().cpu()) < 2e-5
 
 
 # ---- stand-alone op and layer ------------------------------------------------------------------------
