@@ -1,0 +1,164 @@
+"""Multi-GPU partitioning of the SpKBGAT path: one process per GPU, torch.distributed (NCCL
+over NVLink / NVSwitch on B200; gloo for the CPU tests of this host logic).
+
+1-D row partition: rank g owns a contiguous range of aggregation rows (entities) chosen so that every
+rank holds about E/G edges (prefix sum of in-degrees), together with ALL edges whose edge[0] falls in
+the range -- the CSR segmented reduce is then purely local. Per layer and direction there is one
+exchange step:
+    forward : all-gather of the projected gather table P2~ (each rank projects only its own rows)
+    backward: reduce-scatter of the partial dP2~ (the transpose of the all-gather),
+              all-reduce of dP3~ (per relation) and of the weight gradients (KB..MB).
+Gathered node indices are remapped to a padded global numbering  j' = owner(j) * max_rows + (j - lo[owner])
+so that the equal-sized all-gather / reduce-scatter buffers are directly indexable by the kernels.
+The reference has no distributed path (single process, single device); this is new design.
+"""
+import torch
+import torch.distributed as dist
+
+
+def balanced_row_bounds(agg_rows, n_rows, world):
+    """Row split points [world+1] such that each part holds ~len(agg_rows)/world edges.
+    agg_rows: int64 tensor of aggregation rows (edge[0] of every 1-hop and 2-hop edge)."""
+    deg = torch.bincount(agg_rows, minlength=n_rows)
+    cum = torch.cumsum(deg, 0)
+    total = int(cum[-1]) if n_rows else 0
+    targets = torch.tensor([total * g // world for g in range(1, world)], dtype=cum.dtype, device=cum.device)
+    cuts = torch.searchsorted(cum, targets, right=False) + 1 if world > 1 else targets
+    bounds = [0] + [int(c) for c in cuts.clamp(max=n_rows)] + [n_rows]
+    for i in range(1, len(bounds)):                      # monotone, and no empty middle part swallowing the end
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return bounds
+
+
+class RowPartition:
+    """Which rows each rank owns, and the padded global numbering of gathered nodes."""
+
+    def __init__(self, bounds):
+        self.bounds = list(bounds)
+        self.world = len(bounds) - 1
+        self.max_rows = max(1, max(self.bounds[g + 1] - self.bounds[g] for g in range(self.world)))
+
+    def rows_of(self, rank):
+        return self.bounds[rank], self.bounds[rank + 1]
+
+    def remap(self, idx):
+        """Global entity ids -> padded global ids (owner * max_rows + local offset)."""
+        b = torch.tensor(self.bounds, dtype=idx.dtype, device=idx.device)
+        owner = torch.searchsorted(b, idx, right=True) - 1
+        owner = owner.clamp_(0, self.world - 1)
+        return owner * self.max_rows + (idx - b[owner])
+
+    def local_edges(self, rank, edge, edge_type, nhop):
+        """Edges whose aggregation row is owned by `rank`, in original relative order (1-hop block, 2-hop block),
+        with rows made local and gathered nodes remapped. Returns (edge[2,E1'], type[E1'], nhop[E2',4], sel1, sel2)."""
+        lo, hi = self.rows_of(rank)
+        sel1 = ((edge[0] >= lo) & (edge[0] < hi)).nonzero().flatten()
+        e_loc = torch.stack((edge[0, sel1] - lo, self.remap(edge[1, sel1])), dim=0)
+        t_loc = edge_type[sel1]
+        if nhop is not None and nhop.numel() > 0:
+            sel2 = ((nhop[:, 3] >= lo) & (nhop[:, 3] < hi)).nonzero().flatten()
+            nh = nhop[sel2]
+            nh_loc = torch.stack((self.remap(nh[:, 0]), nh[:, 1], nh[:, 2], nh[:, 3] - lo), dim=1)
+        else:
+            sel2 = torch.zeros(0, dtype=torch.int64, device=edge.device)
+            nh_loc = torch.zeros((0, 4), dtype=torch.int64, device=edge.device)
+        return e_loc, t_loc, nh_loc, sel1, sel2
+
+
+class DistContext:
+    """Collectives of the partitioned path; attached to a KGraph as `graph.dist`."""
+
+    def __init__(self, partition, rank, group=None):
+        self.part = partition
+        self.rank = rank
+        self.group = group
+        self.world = partition.world
+
+    @property
+    def n_local(self):
+        lo, hi = self.part.rows_of(self.rank)
+        return hi - lo
+
+    def all_gather_rows(self, local_rows):
+        """[n_local, W] (any row stride) -> [world * max_rows, W] in padded global numbering."""
+        w = local_rows.shape[1]
+        pad = local_rows.new_zeros(self.part.max_rows, w)
+        pad[: local_rows.shape[0]] = local_rows
+        out = local_rows.new_empty(self.world * self.part.max_rows, w)
+        dist.all_gather_into_tensor(out, pad, group=self.group)
+        return out
+
+    def reduce_scatter_rows(self, partial_all, out_local):
+        """Sum over ranks of [world * max_rows, W] partials; this rank's rows land in out_local [n_local, W]."""
+        w = partial_all.shape[1]
+        if dist.get_backend(self.group) == "gloo":           # gloo has no reduce_scatter: all-reduce and slice
+            full = partial_all.contiguous().clone()
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+            chunk = full[self.rank * self.part.max_rows:(self.rank + 1) * self.part.max_rows]
+        else:
+            chunk = partial_all.new_empty(self.part.max_rows, w)
+            dist.reduce_scatter_tensor(chunk, partial_all.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
+        out_local.copy_(chunk[: out_local.shape[0]])
+        return out_local
+
+    def all_reduce(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class PartitionedKBGAT:
+    """SpKBGATModified over a row partition: this rank holds its entity rows (embeddings, outputs, gradients),
+    the replicated relation / attention parameters, and the CSR / CSC layouts of its own edges."""
+
+    def __init__(self, n_ent, n_rel, edge, edge_type, nhop, in_dim, out_dim, nheads, alpha, device,
+                 entity_emb=None, relation_emb=None, seed=0, group=None, state_dict=None):
+        from .models import SpKBGATModified
+        from .graph import KGraph
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = device
+        edge = edge.to(device); edge_type = edge_type.to(device)
+        nhop = nhop.to(device) if nhop is not None and nhop.numel() else None
+        agg = edge[0] if nhop is None else torch.cat((edge[0], nhop[:, 3]))
+        self.part = RowPartition(balanced_row_bounds(agg, n_ent, self.world))
+        del agg
+        lo, hi = self.part.rows_of(self.rank)
+        self.lo, self.hi = lo, hi
+        e_loc, t_loc, nh_loc, _, _ = self.part.local_edges(self.rank, edge, edge_type, nhop)
+        self.n_edges_total = edge.shape[1] + (0 if nhop is None else nhop.shape[0])
+        self.n_edges_local = e_loc.shape[1] + nh_loc.shape[0]
+        del edge, edge_type, nhop
+        g = torch.Generator().manual_seed(seed)
+        if entity_emb is None:
+            entity_emb = torch.randn(n_ent, in_dim, generator=g)
+        if relation_emb is None:
+            relation_emb = torch.randn(n_rel, in_dim, generator=g)
+        torch.manual_seed(seed)                              # identical replicated parameters on every rank
+        self.model = SpKBGATModified(entity_emb[lo:hi].clone(), relation_emb.clone(), [out_dim, 2 * out_dim],
+                                     [out_dim, 2 * out_dim], 0.0, alpha, [nheads, nheads], None)
+        if state_dict is not None:
+            sd = {k: (v[lo:hi] if k in ("entity_embeddings", "final_entity_embeddings") else v) for k, v in state_dict.items()}
+            self.model.load_state_dict(sd)
+        self.model = self.model.to(device)
+        self.graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, hi - lo, n_rel, device=device,
+                            n_cols=self.world * self.part.max_rows)
+        self.graph.dist = DistContext(self.part, self.rank, group)
+        self.batch = torch.arange(hi - lo, device=device)
+        self.g_ent = None
+        self.g_rel = None
+
+    def set_loss_weights(self, g_ent_full, g_rel):
+        self.g_ent = g_ent_full[self.lo:self.hi].to(self.device)
+        self.g_rel = g_rel.to(self.device)
+
+    def step(self):
+        """One forward + backward; loss = <out_entity, G_e> + <out_relation, G_r> with the relation term counted once."""
+        self.model.zero_grad(set_to_none=True)
+        out_e, out_r, _ = self.model(None, self.batch, self.graph, None)
+        if self.g_ent is None:
+            gen = torch.Generator().manual_seed(1)
+            self.g_ent = torch.randn(out_e.shape, generator=gen).to(self.device)
+            self.g_rel = torch.randn(out_r.shape, generator=gen).to(self.device)
+        loss = (out_e * self.g_ent).sum() + (out_r * self.g_rel).sum()
+        loss.backward()
+        return out_e, out_r, loss

@@ -126,9 +126,10 @@ class MatMulFn(torch.autograd.Function):
     """X @ W with the library GEMMs (relation_embed.mm(W) models.py:77, entity_embeddings.mm(W_entities) 175)."""
 
     @staticmethod
-    def forward(ctx, X, W):
+    def forward(ctx, X, W, dist=None):
         X = tc_friendly(X.contiguous()); W = W.contiguous()
         ctx.save_for_backward(X, W)
+        ctx.dist = dist
         return gemm_nn(X, W)
 
     @staticmethod
@@ -137,11 +138,14 @@ class MatMulFn(torch.autograd.Function):
         g = g.contiguous()
         dX = gemm_nn(g, W.t().contiguous()) if ctx.needs_input_grad[0] else None
         dW = gemm_tn(X, g) if ctx.needs_input_grad[1] else None
-        return dX, dW
+        if dW is not None and ctx.dist is not None:
+            ctx.dist.all_reduce(dW)          # X rows are partitioned across ranks
+        return dX, dW, None
 
 
-def matmul(X, W):
-    return MatMulFn.apply(X, W)
+def matmul(X, W, dist=None):
+    """dist: DistContext when X's rows are partitioned across ranks (dW is then all-reduced)."""
+    return MatMulFn.apply(X, W, dist)
 
 
 # ---- fused attention-layer group -------------------------------------------------------------
@@ -179,16 +183,14 @@ def edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanfl
     return out, den, sw
 
 
-def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, dP, dP3):
-    """K3 + K4 launches. Fills dP[:, :Wd] (dP1~), dP[:, Wd:] (dP2~, indexed by gathered node) and dP3 [R, Wd]."""
+def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, dP1, dP2, dP3):
+    """K3 + K4 launches. Fills dP1 [n_rows, Wd], dP2 [n_cols, Wd] (indexed by gathered node) and dP3 [R, Wd]."""
     lib = _lib.load()
     graph.build_backward()
     n, dev = graph.n_nodes, P1.device
     ldg = (geom.Dt + 7) // 8 * 8
     G = torch.empty(n, ldg, dtype=torch.float32, device=dev)
     rec = torch.empty(max(1, graph.n_edges), 2 * geom.H, dtype=torch.float32, device=dev)
-    dP1 = dP[:, :geom.Wd]
-    dP2 = dP[:, geom.Wd:]
     a = _lib.EdgeBwdRowsArgs()
     a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
     a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
@@ -233,24 +235,45 @@ class AttentionGroupFn(torch.autograd.Function):
         X = tc_friendly(X.contiguous()); Wn = Wn.contiguous(); Rel = Rel.contiguous(); Wr = Wr.contiguous()
         P = gemm_nn(X, Wn)                      # [N, 2Wd] = [P1~ | P2~]
         P3 = gemm_nn(Rel, Wr)                   # [R, Wd]
-        out, den, sw = edge_attn_forward(graph, P[:, :geom.Wd], P[:, geom.Wd:], P3, geom, alpha, apply_elu,
-                                         mask_csr, nanflag)
-        ctx.save_for_backward(X, Wn, Rel, Wr, P, P3, out, den)
+        dist = getattr(graph, "dist", None)
+        # multi-GPU: rows are partitioned, the gathered table P2~ is all-gathered over NVLink
+        P2 = dist.all_gather_rows(P[:, geom.Wd:]) if dist is not None else P[:, geom.Wd:]
+        out, den, sw = edge_attn_forward(graph, P[:, :geom.Wd], P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
+        if dist is not None:
+            ctx.save_for_backward(X, Wn, Rel, Wr, P, P3, out, den, P2)
+        else:
+            ctx.save_for_backward(X, Wn, Rel, Wr, P, P3, out, den)
         ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr = graph, geom, alpha, apply_elu, mask_csr
         ctx.mark_non_differentiable(den, sw)
         return out, den, sw
 
     @staticmethod
     def backward(ctx, dout, _dden, _dsw):
-        X, Wn, Rel, Wr, P, P3, out, den = ctx.saved_tensors
         geom, graph = ctx.geom, ctx.graph
+        dist = getattr(graph, "dist", None)
+        if dist is not None:
+            X, Wn, Rel, Wr, P, P3, out, den, P2 = ctx.saved_tensors
+        else:
+            X, Wn, Rel, Wr, P, P3, out, den = ctx.saved_tensors
+            P2 = P[:, geom.Wd:]
         dout = dout.contiguous()
         dP = torch.empty_like(P)
         dP3 = torch.empty_like(P3)
-        edge_attn_backward(graph, P[:, :geom.Wd], P[:, geom.Wd:], P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr,
-                           out, dout, den, dP, dP3)
+        if dist is None:
+            edge_attn_backward(graph, P[:, :geom.Wd], P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr,
+                               out, dout, den, dP[:, :geom.Wd], dP[:, geom.Wd:], dP3)
+        else:
+            # partial dP2~ over ALL gathered nodes -> reduce-scatter to the owners (transpose of the all-gather);
+            # dP3~ (per relation) and the weight gradients are all-reduced
+            dP2_all = torch.empty_like(P2)
+            edge_attn_backward(graph, P[:, :geom.Wd], P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr,
+                               out, dout, den, dP[:, :geom.Wd], dP2_all, dP3)
+            dist.reduce_scatter_rows(dP2_all, dP[:, geom.Wd:])
+            dist.all_reduce(dP3)
         dX = gemm_nn(dP, Wn.t().contiguous()) if ctx.needs_input_grad[0] else None
         dWn = gemm_tn(X, dP) if ctx.needs_input_grad[1] else None
+        if dWn is not None and dist is not None:
+            dist.all_reduce(dWn)
         dRel = gemm_nn(dP3, Wr.t().contiguous()) if ctx.needs_input_grad[2] else None
         dWr = gemm_tn(Rel, dP3) if ctx.needs_input_grad[3] else None
         return dX, dWn, dRel, dWr, None, None, None, None, None, None
