@@ -44,17 +44,10 @@ def b_alg_bytes(n, e1, e2):
     return layer(F_IN, HEADS) + layer(dt, 1)
 
 
-def make_inputs(name, seed=0):
+def make_inputs(name, seed=0, device="cpu"):
     from recon_b200.synth import make_kg
     n, e1, e2, r, alpha, hub_frac = WORKLOADS[name]
-    edge, etype, nhop = make_kg(n, e1, r, alpha, e2, seed)
-    if hub_frac < 1.0:                      # background of uniform rows + Pareto hubs (power-law tail)
-        g = torch.Generator().manual_seed(seed + 100)
-        uni = torch.rand(e1, generator=g) >= hub_frac
-        edge[0] = torch.where(uni, torch.randint(0, n, (e1,), generator=g), edge[0])
-        if e2:
-            uni2 = torch.rand(e2, generator=g) >= hub_frac
-            nhop[:, 3] = torch.where(uni2, torch.randint(0, n, (e2,), generator=g), nhop[:, 3])
+    edge, etype, nhop = make_kg(n, e1, r, alpha, e2, seed, device=device, hub_frac=hub_frac)
     return n, r, edge, etype, nhop
 
 
@@ -159,12 +152,15 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    n, r, edge, etype, nhop = make_inputs(workload)
+    # multi-GPU: every rank generates the same graph on its own device (same seed, same device type)
+    n, r, edge, etype, nhop = make_inputs(workload, device=dev if world > 1 else "cpu")
     e_total = edge.shape[1] + nhop.shape[0]
 
     if world > 1:
         from recon_b200.dist import PartitionedKBGAT
         runner = PartitionedKBGAT(n, r, edge, etype, nhop, F_IN, D_OUT, HEADS, ALPHA, dev)
+        del edge, etype, nhop
+        torch.cuda.empty_cache()
     else:
         runner = SingleGPU(n, r, edge, etype, nhop, dev)
 

@@ -129,12 +129,14 @@ class PartitionedKBGAT:
         self.n_edges_local = e_loc.shape[1] + nh_loc.shape[0]
         del edge, edge_type, nhop
         g = torch.Generator().manual_seed(seed)
-        if entity_emb is None:
-            entity_emb = torch.randn(n_ent, in_dim, generator=g)
         if relation_emb is None:
             relation_emb = torch.randn(n_rel, in_dim, generator=g)
+        if entity_emb is None:                               # synthetic: only this rank's rows are ever materialised
+            ent_loc = torch.randn(hi - lo, in_dim, generator=torch.Generator().manual_seed(seed + 1000 + self.rank))
+        else:
+            ent_loc = entity_emb[lo:hi].clone()
         torch.manual_seed(seed)                              # identical replicated parameters on every rank
-        self.model = SpKBGATModified(entity_emb[lo:hi].clone(), relation_emb.clone(), [out_dim, 2 * out_dim],
+        self.model = SpKBGATModified(ent_loc, relation_emb.clone(), [out_dim, 2 * out_dim],
                                      [out_dim, 2 * out_dim], 0.0, alpha, [nheads, nheads], None)
         if state_dict is not None:
             sd = {k: (v[lo:hi] if k in ("entity_embeddings", "final_entity_embeddings") else v) for k, v in state_dict.items()}

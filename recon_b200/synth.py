@@ -10,30 +10,41 @@ import math
 import torch
 
 
-def zipf_rows(n_nodes, n_edges, alpha, gen):
+def zipf_rows(n_nodes, n_edges, alpha, gen, device="cpu"):
     if alpha is None or math.isinf(alpha):
-        return torch.randint(0, n_nodes, (n_edges,), generator=gen, dtype=torch.int64)
-    u = torch.rand(n_edges, generator=gen, dtype=torch.float64).clamp_(min=1e-12)
+        return torch.randint(0, n_nodes, (n_edges,), generator=gen, dtype=torch.int64, device=device)
+    u = torch.rand(n_edges, generator=gen, dtype=torch.float64, device=device).clamp_(min=1e-12)
     rank = torch.floor(u.pow_(-1.0 / alpha)).clamp_(max=float(n_nodes)).to(torch.int64) - 1
-    perm = torch.randperm(n_nodes, generator=gen)
+    perm = torch.randperm(n_nodes, generator=gen, device=device)
     return perm[rank.clamp_(0, n_nodes - 1)]
 
 
-def make_kg(n_nodes, n_edges, n_rel, alpha=None, n_nhop=0, seed=0):
+def make_kg(n_nodes, n_edges, n_rel, alpha=None, n_nhop=0, seed=0, device="cpu", hub_frac=1.0):
     """Returns (edge int64[2,E1] = [rows(tail); cols(head)], edge_type int64[E1],
-    nhop int64[E2,4] = [s, r1, r2, t] rows with t Zipf / s uniform, like 1-hop)."""
-    gen = torch.Generator().manual_seed(seed)
-    rows = zipf_rows(n_nodes, n_edges, alpha, gen)
-    cols = torch.randint(0, n_nodes, (n_edges,), generator=gen, dtype=torch.int64)
-    etype = torch.randint(0, n_rel, (n_edges,), generator=gen, dtype=torch.int64)
+    nhop int64[E2,4] = [s, r1, r2, t] rows with t Zipf / s uniform, like 1-hop).
+    hub_frac < 1: only that share of the edges gets a Pareto row, the rest uniform rows (a power-law tail over a
+    uniform background). device: generate on that device (same seed + same device type -> same graph on every rank)."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    kw = dict(generator=gen, dtype=torch.int64, device=device)
+
+    def agg_rows(m):
+        rows = zipf_rows(n_nodes, m, alpha, gen, device)
+        if hub_frac < 1.0:
+            uni = torch.rand(m, generator=gen, device=device) >= hub_frac
+            rows = torch.where(uni, torch.randint(0, n_nodes, (m,), **kw), rows)
+        return rows
+
+    rows = agg_rows(n_edges)
+    cols = torch.randint(0, n_nodes, (n_edges,), **kw)
+    etype = torch.randint(0, n_rel, (n_edges,), **kw)
     edge = torch.stack((rows, cols), dim=0)
     if n_nhop > 0:
-        t = zipf_rows(n_nodes, n_nhop, alpha, gen)
-        s = torch.randint(0, n_nodes, (n_nhop,), generator=gen, dtype=torch.int64)
-        r = torch.randint(0, n_rel, (n_nhop, 2), generator=gen, dtype=torch.int64)
+        t = agg_rows(n_nhop)
+        s = torch.randint(0, n_nodes, (n_nhop,), **kw)
+        r = torch.randint(0, n_rel, (n_nhop, 2), **kw)
         nhop = torch.stack((s, r[:, 0], r[:, 1], t), dim=1)
     else:
-        nhop = torch.zeros((0, 4), dtype=torch.int64)
+        nhop = torch.zeros((0, 4), dtype=torch.int64, device=device)
     return edge, etype, nhop
 
 

@@ -350,3 +350,52 @@ def test_training_mode_dropout_runs_and_is_unbiased_in_shape():
     # eval mode: no dropout. (Not bit-equal: every forward re-normalises entity_embeddings.data in place,
     # models.py:160-161, and normalize(normalize(x)) differs from normalize(x) in the last ulp.)
     assert torch.allclose(a, b, atol=1e-6)
+
+
+# ---- K0b: batch adjacency + 2-hop rows, bit-exact with Corpus (values and order) -----------------------
+@pytest.mark.parametrize("name", ["edges_a", "edges_b", "edges_partial"])
+def test_batch_edges_match_corpus_golden(name):
+    from recon_b200.nhop import TripleGraph
+    g = load_golden(name)
+    tr = torch.as_tensor(g["triples"])
+    n = int(tr[:, [0, 2]].max()) + 1
+    tg = TripleGraph(tr, n, device=dev())
+    partial = bool(g["partial"])
+    idx, val, nhop = tg.batch_edges(g["batch"].tolist(), partial)
+    assert np.array_equal(idx.cpu().numpy(), g["adj_idx"])
+    assert np.array_equal(val.cpu().numpy(), g["adj_val"])
+    assert np.array_equal(nhop.cpu().numpy(), g["nhop"].astype(np.int32))
+    fidx, fval, fnhop = tg.batch_edges(list(range(n)), partial)
+    assert np.array_equal(fidx.cpu().numpy(), g["full_adj_idx"])
+    assert np.array_equal(fval.cpu().numpy(), g["full_adj_val"])
+    assert np.array_equal(fnhop.cpu().numpy(), g["full_nhop"].astype(np.int32))
+
+
+def test_batch_edges_toy_kg():
+    from recon_b200.nhop import build_batch_edges
+    tr = torch.as_tensor(load_golden("edges_toy")["triples"]).to(dev())
+    idx, val, nhop = build_batch_edges(tr, 10, [0, 1, 2, 3])
+    assert idx.cpu().tolist() == [[1, 1, 2, 3, 0, 3, 4], [0, 0, 0, 1, 1, 2, 3]]
+    assert val.cpu().tolist() == [5, 6, 7, 8, 2, 9, 1]
+    assert nhop.cpu().tolist() == [[0, 5, 8, 3], [1, 8, 1, 4], [1, 2, 7, 2], [2, 9, 1, 4]]
+
+
+def test_batch_edges_vs_oracle_random_medium():
+    """Larger random KG with multi-edges / self loops against the pure-Python restatement of Corpus."""
+    from recon_b200.nhop import TripleGraph
+    from recon_b200.synth import make_triples
+    from oracle import edges as OE
+    n, t, r = 400, 3000, 9
+    tr = make_triples(n, t, r, seed=9)
+    graph = OE.build_graph(*OE.triples_to_adj(tr.tolist()))
+    gen = torch.Generator().manual_seed(3)
+    batch = torch.randperm(n, generator=gen)[:150].tolist() + [5, 5]       # duplicates allowed
+    want_idx, want_val = OE.batch_adj(graph, batch)
+    want_nhop = OE.batch_nhop(graph, batch)
+    idx, val, nhop = TripleGraph(tr, n, device=dev()).batch_edges(batch)
+    assert idx.cpu().tolist() == want_idx and val.cpu().tolist() == want_val
+    assert nhop.cpu().tolist() == want_nhop
+    # and the model consumes them directly
+    from recon_b200 import KGraph
+    kg = KGraph(idx, val, nhop.long(), n, r, device=dev())
+    assert kg.n_edges == len(want_val) + len(want_nhop)
