@@ -235,6 +235,9 @@ def main():
         base = cpu_reference_arm(3, 1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 class SingleGPU:

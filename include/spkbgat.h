@@ -131,7 +131,8 @@ typedef struct {
     const float* G; int64_t ldg;
     const float* rec;
     float* out; int64_t ldout;                   /* [n_seg, width] */
-    int32_t n_seg; int32_t reserved;
+    int32_t n_seg;
+    int32_t flags;                               /* bit 0: many short segments -> 32-segments-per-warp streaming kernel */
     spk_geom geom;
     spk_hub_tasks hub;
 } spk_seg_gather_args;

@@ -57,7 +57,7 @@ class SegGatherArgs(C.Structure):
     _fields_ = [("segptr", C.c_void_p), ("src", C.c_void_p), ("pos", C.c_void_p),
                 ("G", C.c_void_p), ("ldg", C.c_int64), ("rec", C.c_void_p),
                 ("out", C.c_void_p), ("ldout", C.c_int64),
-                ("n_seg", C.c_int32), ("reserved", C.c_int32),
+                ("n_seg", C.c_int32), ("flags", C.c_int32),
                 ("geom", Geom), ("hub", HubTasks)]
 
 

@@ -206,7 +206,7 @@ int spk_edge_attn_bwd_segments(const spk_seg_gather_args* p, spk_stream_t stream
         return 1;
     }
     a.segptr = p->segptr; a.src = p->src; a.pos = p->pos; a.G = p->G; a.ldg = p->ldg; a.rec = p->rec;
-    a.outp = p->out; a.ldout = p->ldout; a.n_seg = p->n_seg;
+    a.outp = p->out; a.ldout = p->ldout; a.n_seg = p->n_seg; a.prefer_stream = p->flags & 1;
     a.hub = hub_of(p->hub);
     if (a.hub.n_tasks > 0 && (a.hub.ldpart < p->geom.width || (a.hub.ldpart & 3) || !aligned16(a.hub.partial))) {
         set_error("edge_attn_bwd_segments: hub partial buffer needs ldpart >= width");

@@ -68,6 +68,7 @@ struct SegGatherArgs {
     const float* rec;         // [E, 2H]
     float* outp; long ldout;  // [n_seg, Wd]  sum w*G[src] | sum ds | 0
     int n_seg;
+    int prefer_stream;        // many short segments (avg < ~5 entries): use the 32-segments-per-warp streaming kernel
     LayerGeom g;
     HubTasks hub;             // partial: [n_tasks, Wd + 4]
 };

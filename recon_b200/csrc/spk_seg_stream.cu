@@ -235,11 +235,13 @@ int launch_n(const SegGatherArgs& a, cudaStream_t s) {
 }  // namespace
 
 int launch_seg_gather_stream(const SegGatherArgs& a, cudaStream_t s) {
-    // Opt-in (SPK_SEG_STREAM=1): measured on B200 at C2 the register-gather kernel is faster for this pass (cols 4.9 ms vs
-    // 5.8 ms, relation segments 3.1 ms vs 6.1 ms per launch) -- it is light enough (74 registers) not to be occupancy-bound.
+    // Used when the caller flags many short segments (multi-GPU CSC: ~2.5 entries per gathered node, where a warp per
+    // segment wastes the machine) or with SPK_SEG_STREAM=1. At C2 on one GPU (10 entries per segment) the register-gather
+    // kernel measured faster (cols 4.9 vs 5.8 ms, relation segments 3.1 vs 6.1 ms per launch): it is light enough
+    // (74 registers) not to be occupancy-bound.
     static int enabled = -1;
     if (enabled < 0) { const char* e = getenv("SPK_SEG_STREAM"); enabled = (e && e[0] == '1') ? 1 : 0; }
-    if (!enabled || (a.ldg % 4) != 0) return -1;
+    if (!(enabled || a.prefer_stream) || (a.ldg % 4) != 0) return -1;
     switch ((a.g.Wd4 + 31) / 32) {
         case 1: return launch_n<1>(a, s);
         case 2: return launch_n<2>(a, s);

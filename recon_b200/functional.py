@@ -214,6 +214,7 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
         s.segptr = ptr.data_ptr(); s.src = src.data_ptr(); s.pos = pos.data_ptr()
         s.G = G.data_ptr(); s.ldg = ldg; s.rec = rec.data_ptr()
         s.out = dst.data_ptr(); s.ldout = dst.stride(0); s.n_seg = n_seg
+        s.flags = 1 if (n_seg > 0 and src.numel() < 5 * n_seg) else 0        # many short segments -> streaming kernel
         s.geom = geom.struct()
         part = _hub_partial(hubs, geom.Wd, dev)
         hubs.fill(s.hub, part, geom.Wd)
@@ -228,52 +229,91 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
 
 
 class AttentionGroupFn(torch.autograd.Function):
-    """One fused group of <=4 heads: (X, Wn, Rel, Wr) -> ELU?(attention output) [N, H*D]."""
+    """One fused group of <=4 heads: (X, Wn, Rel, Wr) -> ELU?(attention output) [N, H*D].
+
+    Multi-GPU (graph.dist set): rows are partitioned; the gathered table P2~ must cover all nodes.
+      * "proj"  exchange: all-gather the projected rows P2~ [n, Wd]; backward reduce-scatters the partial dP2~.
+      * "input" exchange (chosen when the input is narrower than the projection, i.e. layer 1: F=50 vs Wd=208):
+        all-gather X [n, F] and project all nodes locally (cheap on the tensor cores); backward projects the partial
+        dP2~ back to input space and reduce-scatters [n, F]. 4x fewer bytes over NVLink for layer 1.
+    """
 
     @staticmethod
     def forward(ctx, X, Wn, Rel, Wr, graph, geom, alpha, apply_elu, mask_csr, nanflag):
         X = tc_friendly(X.contiguous()); Wn = Wn.contiguous(); Rel = Rel.contiguous(); Wr = Wr.contiguous()
-        P = gemm_nn(X, Wn)                      # [N, 2Wd] = [P1~ | P2~]
-        P3 = gemm_nn(Rel, Wr)                   # [R, Wd]
         dist = getattr(graph, "dist", None)
-        # multi-GPU: rows are partitioned, the gathered table P2~ is all-gathered over NVLink (SURVEY.md 8e)
-        P2 = dist.all_gather_rows(P[:, geom.Wd:]) if dist is not None else P[:, geom.Wd:]
-        out, den, sw = edge_attn_forward(graph, P[:, :geom.Wd], P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
-        if dist is not None:
-            ctx.save_for_backward(X, Wn, Rel, Wr, P, P3, out, den, P2)
+        Wd = geom.Wd
+        P3 = gemm_nn(Rel, Wr)                   # [R, Wd]
+        mode = "local"
+        X_all = None
+        if dist is None:
+            P = gemm_nn(X, Wn)                  # [N, 2Wd] = [P1~ | P2~]
+            P1, P2 = P[:, :Wd], P[:, Wd:]
+        elif 2 * X.shape[1] <= Wd:
+            mode = "input"
+            X_all = tc_friendly(dist.all_gather_rows(X))
+            P1 = gemm_nn(X, Wn[:, :Wd])
+            P2 = gemm_nn(X_all, Wn[:, Wd:])     # every rank projects all nodes
         else:
-            ctx.save_for_backward(X, Wn, Rel, Wr, P, P3, out, den)
-        ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr = graph, geom, alpha, apply_elu, mask_csr
+            mode = "proj"
+            P = gemm_nn(X, Wn)
+            P1 = P[:, :Wd]
+            P2 = dist.all_gather_rows(P[:, Wd:])
+        out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
+        ctx.save_for_backward(X, Wn, Rel, Wr, P1, P2, P3, out, den, X_all if X_all is not None else X.new_empty(0))
+        ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, ctx.mode = graph, geom, alpha, apply_elu, mask_csr, mode
         ctx.mark_non_differentiable(den, sw)
         return out, den, sw
 
     @staticmethod
     def backward(ctx, dout, _dden, _dsw):
-        geom, graph = ctx.geom, ctx.graph
+        geom, graph, mode = ctx.geom, ctx.graph, ctx.mode
         dist = getattr(graph, "dist", None)
-        if dist is not None:
-            X, Wn, Rel, Wr, P, P3, out, den, P2 = ctx.saved_tensors
-        else:
-            X, Wn, Rel, Wr, P, P3, out, den = ctx.saved_tensors
-            P2 = P[:, geom.Wd:]
+        X, Wn, Rel, Wr, P1, P2, P3, out, den, X_all = ctx.saved_tensors
+        Wd = geom.Wd
         dout = dout.contiguous()
-        dP = torch.empty_like(P)
+        n = X.shape[0]
         dP3 = torch.empty_like(P3)
-        if dist is None:
-            edge_attn_backward(graph, P[:, :geom.Wd], P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr,
-                               out, dout, den, dP[:, :geom.Wd], dP[:, geom.Wd:], dP3)
-        else:
-            # partial dP2~ over ALL gathered nodes -> reduce-scatter to the owners (transpose of the all-gather);
-            # dP3~ (per relation) and the weight gradients are all-reduced
-            dP2_all = torch.empty_like(P2)
-            edge_attn_backward(graph, P[:, :geom.Wd], P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr,
-                               out, dout, den, dP[:, :geom.Wd], dP2_all, dP3)
-            dist.reduce_scatter_rows(dP2_all, dP[:, geom.Wd:])
+        WnT = Wn.t().contiguous()               # [2Wd, F]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dX = dWn = None
+        if mode == "local":
+            dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=X.device)
+            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den,
+                               dP[:, :Wd], dP[:, Wd:], dP3)
+            if need_x:
+                dX = gemm_nn(dP, WnT)
+            if need_w:
+                dWn = gemm_tn(X, dP)
+        elif mode == "proj":
+            dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=X.device)
+            dP2_all = torch.empty_like(P2)      # partial over this rank's edges, all gathered nodes
+            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den,
+                               dP[:, :Wd], dP2_all, dP3)
+            dist.reduce_scatter_rows(dP2_all, dP[:, Wd:])
+            del dP2_all
             dist.all_reduce(dP3)
-        dX = gemm_nn(dP, Wn.t().contiguous()) if ctx.needs_input_grad[0] else None
-        dWn = gemm_tn(X, dP) if ctx.needs_input_grad[1] else None
-        if dWn is not None and dist is not None:
-            dist.all_reduce(dWn)
+            if need_x:
+                dX = gemm_nn(dP, WnT)
+            if need_w:
+                dWn = dist.all_reduce(gemm_tn(X, dP))
+        else:                                   # "input"
+            dP1 = torch.empty(n, Wd, dtype=torch.float32, device=X.device)
+            dP2_all = torch.empty_like(P2)
+            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den,
+                               dP1, dP2_all, dP3)
+            dist.all_reduce(dP3)
+            if need_x:
+                dX2_all = gemm_nn(dP2_all, WnT[Wd:])            # partial dX of every node through the gathered side
+                dX = torch.empty(n, X.shape[1], dtype=torch.float32, device=X.device)
+                dist.reduce_scatter_rows(dX2_all, dX)
+                del dX2_all
+                gemm_nn(dP1, WnT[:Wd], out=dX, accumulate=True)
+            if need_w:
+                dWn = torch.empty_like(Wn)
+                gemm_tn(X, dP1, out=dWn[:, :Wd])
+                gemm_tn(X_all, dP2_all, out=dWn[:, Wd:])
+                dist.all_reduce(dWn)
         dRel = gemm_nn(dP3, Wr.t().contiguous()) if ctx.needs_input_grad[2] else None
         dWr = gemm_tn(Rel, dP3) if ctx.needs_input_grad[3] else None
         return dX, dWn, dRel, dWr, None, None, None, None, None, None
