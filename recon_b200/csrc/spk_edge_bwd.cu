@@ -10,6 +10,7 @@
 //   which is dP2~ (per gathered node) resp. dP3~ (per relation).
 // Both are deterministic: fixed edge order inside a segment, hub segments split into chunks whose
 // partials are added in chunk order.
+#include <stdlib.h>
 #include "spk_edge.cuh"
 #include "spk_edge_bwd.cuh"
 
@@ -225,10 +226,9 @@ struct SegAcc {
     float vs[SPK_MAX_HEADS];     // lane-local partial sums of ds (reduced across the warp at the end)
 };
 
-template <int NCH>
+template <int NCH, int U>
 __device__ __forceinline__ void seg_accumulate(const SegGatherArgs& a, int beg, int end, int lane,
                                                const int (&hc)[NCH], SegAcc<NCH>& st) {
-    constexpr int U = (NCH <= 2) ? 4 : 2;
     const LayerGeom g = a.g;
     for (int base = beg; base < end; base += 32) {
         const int n = min(32, end - base);
@@ -302,8 +302,8 @@ __device__ __forceinline__ void seg_store(float* dst, const LayerGeom& g, int la
     }
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(SPK_CTA_THREADS)
+template <int NCH, int U, int MINB>
+__global__ void __launch_bounds__(SPK_CTA_THREADS, MINB)
 seg_gather_kernel(const SegGatherArgs a) {
     const int lane = threadIdx.x & 31;
     const int seg = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -313,14 +313,14 @@ seg_gather_kernel(const SegGatherArgs a) {
     int hc[NCH];
     SegAcc<NCH> st;
     seg_init<NCH>(a.g, lane, hc, st);
-    seg_accumulate<NCH>(a, beg, end, lane, hc, st);
+    seg_accumulate<NCH, U>(a, beg, end, lane, hc, st);
 #pragma unroll
     for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] = warp_sum(st.vs[h]);
     seg_store<NCH>(a.outp + (long)seg * a.ldout, a.g, lane, st);
 }
 
-template <int NCH>
-__global__ void __launch_bounds__(SPK_CTA_THREADS)
+template <int NCH, int U, int MINB>
+__global__ void __launch_bounds__(SPK_CTA_THREADS, MINB)
 seg_gather_tasks_kernel(const SegGatherArgs a) {
     const int lane = threadIdx.x & 31;
     const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
@@ -328,7 +328,7 @@ seg_gather_tasks_kernel(const SegGatherArgs a) {
     int hc[NCH];
     SegAcc<NCH> st;
     seg_init<NCH>(a.g, lane, hc, st);
-    seg_accumulate<NCH>(a, __ldg(a.hub.task_beg + task), __ldg(a.hub.task_end + task), lane, hc, st);
+    seg_accumulate<NCH, U>(a, __ldg(a.hub.task_beg + task), __ldg(a.hub.task_end + task), lane, hc, st);
 #pragma unroll
     for (int h = 0; h < SPK_MAX_HEADS; ++h) st.vs[h] = warp_sum(st.vs[h]);
     seg_store<NCH>(a.hub.partial + (long)task * a.hub.ldpart, a.g, lane, st);
@@ -352,16 +352,37 @@ seg_gather_hub_finalize_kernel(const SegGatherArgs a) {
     }
 }
 
+// tuning variant (unroll depth U, min CTAs per SM): SPK_SEG_VARIANT=0..3, default chosen from B200 measurements
+static int seg_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_SEG_VARIANT"); v = e ? atoi(e) : 1; if (v < 0 || v > 6) v = 1; }
+    return v;
+}
+
 template <int NCH>
 static int launch_seg_t(const SegGatherArgs& a, cudaStream_t s) {
+    constexpr int U0 = (NCH <= 2) ? 4 : 2;
+    const int var = seg_variant();
     if (a.n_seg > 0) {
         const unsigned grid = (a.n_seg + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        seg_gather_kernel<NCH><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (var == 1) seg_gather_kernel<NCH, U0, 4><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 4) seg_gather_kernel<NCH, U0, 5><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 5) seg_gather_kernel<NCH, U0, 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 6) seg_gather_kernel<NCH, (U0 > 2 ? U0 / 2 : U0), 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 2) seg_gather_kernel<NCH, 2 * U0, 2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 3) seg_gather_kernel<NCH, 2 * U0, 3><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else seg_gather_kernel<NCH, U0, 3><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("seg_gather")) return rc;
     }
     if (a.hub.n_tasks > 0) {
         const unsigned grid = (a.hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        seg_gather_tasks_kernel<NCH><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (var == 1) seg_gather_tasks_kernel<NCH, U0, 4><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 4) seg_gather_tasks_kernel<NCH, U0, 5><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 5) seg_gather_tasks_kernel<NCH, U0, 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 6) seg_gather_tasks_kernel<NCH, (U0 > 2 ? U0 / 2 : U0), 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 2) seg_gather_tasks_kernel<NCH, 2 * U0, 2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else if (var == 3) seg_gather_tasks_kernel<NCH, 2 * U0, 3><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        else seg_gather_tasks_kernel<NCH, U0, 3><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("seg_gather_tasks")) return rc;
         seg_gather_hub_finalize_kernel<NCH><<<a.hub.n_hubs, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("seg_gather_hub_finalize")) return rc;

@@ -142,9 +142,12 @@ class PartitionedKBGAT:
             sd = {k: (v[lo:hi] if k in ("entity_embeddings", "final_entity_embeddings") else v) for k, v in state_dict.items()}
             self.model.load_state_dict(sd)
         self.model = self.model.to(device)
+        self.n_rel = n_rel
+        self.group = group
         self.graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, hi - lo, n_rel, device=device,
                             n_cols=self.world * self.part.max_rows)
         self.graph.dist = DistContext(self.part, self.rank, group)
+        self._local_edges_dev = (e_loc, t_loc, nh_loc)
         self.batch = torch.arange(hi - lo, device=device)
         self.g_ent = None
         self.g_rel = None
@@ -153,10 +156,34 @@ class PartitionedKBGAT:
         self.g_ent = g_ent_full[self.lo:self.hi].to(self.device)
         self.g_rel = g_rel.to(self.device)
 
-    def step(self):
+    def e2e(self, steps):
+        """End-to-end step with HOST edge tensors: pinned H2D of this rank's int64 edge list, device CSR / CSC /
+        relation rebuild, forward + backward, loss read-back. Returns (seconds per step, h2d bytes per step)."""
+        import time
+        from .graph import KGraph
+        host = tuple(t.cpu().pin_memory() for t in self._local_edges_dev)
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        res = torch.empty(1, dtype=torch.float32).pin_memory()
+        times = []
+        for i in range(steps + 1):
+            dist.barrier(group=self.group)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e_loc, t_loc, nh_loc = (t.to(self.device, non_blocking=True) for t in host)
+            graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, self.hi - self.lo, self.n_rel,
+                           device=self.device, n_cols=self.world * self.part.max_rows)
+            graph.dist = self.graph.dist
+            _, _, loss = self.step(graph)
+            res.copy_(loss.detach().reshape(1), non_blocking=True)
+            torch.cuda.synchronize()
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+        return sum(times) / len(times), h2d
+
+    def step(self, graph=None):
         """One forward + backward; loss = <out_entity, G_e> + <out_relation, G_r> with the relation term counted once."""
         self.model.zero_grad(set_to_none=True)
-        out_e, out_r, _ = self.model(None, self.batch, self.graph, None)
+        out_e, out_r, _ = self.model(None, self.batch, graph if graph is not None else self.graph, None)
         if self.g_ent is None:
             gen = torch.Generator().manual_seed(1)
             self.g_ent = torch.randn(out_e.shape, generator=gen).to(self.device)
