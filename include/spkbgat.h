@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* spk_stream_t;              /* cudaStream_t */
 
-#define SPK_ABI_VERSION 1
+#define SPK_ABI_VERSION 2
 int spk_abi_version(void);
 const char* spk_last_error(void);
 int64_t spk_launch_count(void);          /* kernels launched through this library so far */
@@ -83,6 +83,12 @@ int64_t spk_gemm_tc_workspace_floats(int32_t N, int32_t K);
 int spk_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                    int64_t M, int32_t N, int32_t K, int32_t accumulate, float* workspace, spk_stream_t stream);
 
+/* Same, with an epilogue on the final value: act = 0 none, 1 = ELU (F.elu at GAT/layers.py:175 / models.py:86). */
+int spk_gemm_nn_tc_act(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                       int64_t M, int32_t N, int32_t K, int32_t accumulate, int32_t act, float* workspace,
+                       spk_stream_t stream);
+int spk_elu_inplace(float* x, int64_t ldx, int64_t n_rows, int32_t width, spk_stream_t stream);
+
 /* C[Ka,Nb] (+)= A[M,Ka]^T * B[M,Nb] on tcgen05 (MN-major operands, both split hi/lo in shared memory),
  * one CTA per (tile, m-split), partials added in split order. */
 int32_t spk_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb);
@@ -137,6 +143,61 @@ typedef struct {
     spk_hub_tasks hub;
 } spk_seg_gather_args;
 int spk_edge_attn_bwd_segments(const spk_seg_gather_args* args, spk_stream_t stream);
+
+/* ---- K2'/K3': "aggregate-then-project" variant for layer groups whose input is narrower than their projection
+ *      (layer 1: in=50, nrela=50 against heads*out=200). Same reference lines as K2/K3 (GAT/layers.py:124-175 and
+ *      their autograd); the sum over a row's edges is linear in [x_i | x_j | r_k], so the edges gather the INPUT
+ *      rows and a.mm(.) (layers.py:137) is applied once per row to the aggregate by spk_gemm_nn_tc_act:
+ *          Zn_h[i] = [ (sum w) x_i | sum w x_j | sum w r_k ] / sum ee      out_h = ELU(Zn_h . a_h^T)
+ *      Table rows ("X~", "Rel~"), built by spk_agg_table: [ x | 0-pad to 4*chunks | 4 score scalars | 0-pad ];
+ *      X~ scalars = (q2_0, q2_1, q1_0, q1_1), Rel~ scalars = (q3_0, q3_1, 0, 0), q* = x . (A*^T a_2^T).
+ *      Needs n_heads <= 2, f_chunks <= 15, r_chunks <= 15. ---- */
+typedef struct {
+    int32_t n_heads;   /* 1..2 */
+    int32_t f_chunks;  /* ceil(in_features / 4) */
+    int32_t r_chunks;  /* ceil(nrela_dim / 4) */
+    int32_t lz;        /* 4 * (2*f_chunks + r_chunks): floats of Zn per head */
+} spk_agg_geom;
+/* T[i, :ldt] = [ X[i, :F] | 0 | X[i] . V[:, 0..3] | 0 ],  V is [F, 4] contiguous, ldt >= 4*f_chunks + 4 */
+int spk_agg_table(const float* X, int64_t ldx, const float* V, float* T, int64_t ldt, int64_t n_rows,
+                  int32_t F, int32_t f_chunks, spk_stream_t stream);
+typedef struct {
+    const int32_t* segptr; const int32_t* col; const int32_t* t1; const int32_t* t2;
+    const float* xrow; int64_t ldxr;             /* X~ of the aggregation rows */
+    const float* xcol; int64_t ldxc;             /* X~ of the gathered nodes */
+    const float* rel; int64_t ldr;               /* Rel~ */
+    const float* mask; int64_t mask_stride;      /* [H][E] CSR-order dropout multipliers or null */
+    float* z; int64_t ldz;                       /* [n_rows, H*lz] */
+    float* den; float* sw;                       /* [n_rows, H] */
+    int32_t* nanflag;
+    int32_t n_rows; float alpha;
+    spk_agg_geom geom;
+    spk_hub_tasks hub;                           /* partial: [n_tasks, 264] */
+} spk_agg_fwd_args;
+int spk_agg_fwd(const spk_agg_fwd_args* args, spk_stream_t stream);
+/* dhn = dout * ELU'(hn) (from the saved output), dden_h = -(dhn_h . hn_h) / den_h */
+int spk_agg_bwd_pre(const float* out, const float* dout, int64_t ldo, const float* den, int32_t n_heads, int32_t d_head,
+                    int32_t apply_elu, float* dhn, int64_t ldd, float* dden, int64_t n_rows, spk_stream_t stream);
+typedef struct {
+    const int32_t* segptr; const int32_t* col; const int32_t* t1; const int32_t* t2;
+    const float* xrow; int64_t ldxr; const float* xcol; int64_t ldxc; const float* rel; int64_t ldr;
+    const float* mask; int64_t mask_stride;
+    const float* dz; int64_t ldz;                /* [n_rows, H*lz] gradient w.r.t. Zn (= dhn . a_h) */
+    const float* den; const float* sw; const float* dden;
+    float* gx; int64_t ldgx;                     /* [n_rows, H*4*f_chunks] rows gathered by the column pass (K4) */
+    float* gr; int64_t ldgr;                     /* [n_rows, H*4*r_chunks] rows gathered by the relation pass (K4) */
+    float* rowout; int64_t ldro;                 /* [n_rows, 4*f_chunks+4]: dX row part | dq1_0 dq1_1 0 0 */
+    float* rowsc;                                /* [n_rows, 8] scratch (per-row scalars between the two kernels) */
+    float* rec;                                  /* [E, 2H] (w, ds) */
+    int32_t n_rows; float alpha;
+    spk_agg_geom geom;
+    spk_hub_tasks hub;                           /* partial: [n_tasks, 8] */
+} spk_agg_bwd_args;
+int spk_agg_bwd_rows(const spk_agg_bwd_args* args, spk_stream_t stream);
+/* dX[i,f] = rowout[i,f] + sum_h dxc[i, h*4*f_chunks + f] + sum_c dq[i,c] V[f,c]; also emits dq [n,4] = (dq2_0,dq2_1,dq1_0,dq1_1).
+ * dxc is the K4 column-pass output with geometry (H, d_head = d_pad = 4*f_chunks). */
+int spk_agg_dx(const float* rowout, int64_t ldro, const float* dxc, int64_t ldc, const float* V, int64_t n_rows,
+               int32_t F, int32_t f_chunks, int32_t n_heads, float* dX, int64_t lddx, float* dq, spk_stream_t stream);
 
 /* ---- stand-alone SpecialSpmmFunctionFinal (layers.py:51-79): out[i,:] = sum_{e in seg i} w[perm[e],:] ---- */
 int spk_spmm_rowsum_fwd(const int32_t* segptr, const int32_t* perm, const float* w, int64_t ldw, int32_t width,

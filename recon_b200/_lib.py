@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f32p = C.POINTER(C.c_float)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Geom(C.Structure):
@@ -61,6 +61,34 @@ class SegGatherArgs(C.Structure):
                 ("geom", Geom), ("hub", HubTasks)]
 
 
+class AggGeom(C.Structure):
+    _fields_ = [("n_heads", C.c_int32), ("f_chunks", C.c_int32), ("r_chunks", C.c_int32), ("lz", C.c_int32)]
+
+
+class AggFwdArgs(C.Structure):
+    _fields_ = [("segptr", C.c_void_p), ("col", C.c_void_p), ("t1", C.c_void_p), ("t2", C.c_void_p),
+                ("xrow", C.c_void_p), ("ldxr", C.c_int64), ("xcol", C.c_void_p), ("ldxc", C.c_int64),
+                ("rel", C.c_void_p), ("ldr", C.c_int64),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int64),
+                ("z", C.c_void_p), ("ldz", C.c_int64), ("den", C.c_void_p), ("sw", C.c_void_p),
+                ("nanflag", C.c_void_p),
+                ("n_rows", C.c_int32), ("alpha", C.c_float),
+                ("geom", AggGeom), ("hub", HubTasks)]
+
+
+class AggBwdArgs(C.Structure):
+    _fields_ = [("segptr", C.c_void_p), ("col", C.c_void_p), ("t1", C.c_void_p), ("t2", C.c_void_p),
+                ("xrow", C.c_void_p), ("ldxr", C.c_int64), ("xcol", C.c_void_p), ("ldxc", C.c_int64),
+                ("rel", C.c_void_p), ("ldr", C.c_int64),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int64),
+                ("dz", C.c_void_p), ("ldz", C.c_int64),
+                ("den", C.c_void_p), ("sw", C.c_void_p), ("dden", C.c_void_p),
+                ("gx", C.c_void_p), ("ldgx", C.c_int64), ("gr", C.c_void_p), ("ldgr", C.c_int64),
+                ("rowout", C.c_void_p), ("ldro", C.c_int64), ("rowsc", C.c_void_p), ("rec", C.c_void_p),
+                ("n_rows", C.c_int32), ("alpha", C.c_float),
+                ("geom", AggGeom), ("hub", HubTasks)]
+
+
 _VP, _I64, _I32 = C.c_void_p, C.c_int64, C.c_int32
 
 # name -> (restype, argtypes); every symbol include/spkbgat.h declares
@@ -79,6 +107,13 @@ SIGNATURES = {
     "spk_gemm_nn_tc_supported": (_I32, [_VP, _I64, _I64, _I32, _I32]),
     "spk_gemm_tc_workspace_floats": (_I64, [_I32, _I32]),
     "spk_gemm_nn_tc": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),
+    "spk_gemm_nn_tc_act": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _I32, _VP, _VP]),
+    "spk_elu_inplace": (_I32, [_VP, _I64, _I64, _I32, _VP]),
+    "spk_agg_table": (_I32, [_VP, _I64, _VP, _VP, _I64, _I64, _I32, _I32, _VP]),
+    "spk_agg_fwd": (_I32, [C.POINTER(AggFwdArgs), _VP]),
+    "spk_agg_bwd_pre": (_I32, [_VP, _VP, _I64, _VP, _I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP]),
+    "spk_agg_bwd_rows": (_I32, [C.POINTER(AggBwdArgs), _VP]),
+    "spk_agg_dx": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I32, _I32, _I32, _VP, _I64, _VP, _VP]),
     "spk_gemm_tn_tc_supported": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _I32]),
     "spk_gemm_tn_tc_workspace_floats": (_I64, [_I64, _I32, _I32]),
     "spk_gemm_tn_tc": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I32, _I32, _I32, _VP, _VP]),

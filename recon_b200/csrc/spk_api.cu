@@ -3,6 +3,7 @@
 #include "../../include/spkbgat.h"
 #include "spk_common.cuh"
 #include "spk_edge.cuh"
+#include "spk_agg.cuh"
 #include "spk_gemm.cuh"
 #include "spk_graph.cuh"
 #include "spk_rowops.cuh"
@@ -142,6 +143,19 @@ int spk_gemm_nn_tc(const float* A, int64_t lda, const float* B, int64_t ldb, flo
     return gemm_nn_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, workspace, (cudaStream_t)stream);
 }
 
+int spk_gemm_nn_tc_act(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                       int64_t M, int32_t N, int32_t K, int32_t accumulate, int32_t act, float* workspace, spk_stream_t stream) {
+    if (lda < K || ldb < N || ldc < N) { set_error("gemm_nn_tc_act: leading dimension too small"); return 1; }
+    if (!gemm_nn_tc_supported(A, lda, M, N, K)) { set_error("gemm_nn_tc_act: A must be 16-byte aligned with lda %% 4 == 0"); return 1; }
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15)) { set_error("gemm_nn_tc_act: aligned workspace required"); return 1; }
+    if (act < 0 || act > 1) { set_error("gemm_nn_tc_act: unknown activation %d", act); return 1; }
+    return gemm_nn_tc(A, lda, B, ldb, C, ldc, M, N, K, accumulate, workspace, (cudaStream_t)stream, act);
+}
+int spk_elu_inplace(float* x, int64_t ldx, int64_t n_rows, int32_t width, spk_stream_t stream) {
+    if (ldx < width) { set_error("elu_inplace: leading dimension too small"); return 1; }
+    return launch_elu_inplace(x, ldx, n_rows, width, (cudaStream_t)stream);
+}
+
 int32_t spk_gemm_tn_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int32_t Ka, int32_t Nb) {
     return gemm_tn_tc_supported(A, lda, B, ldb, M, Ka, Nb);
 }
@@ -213,6 +227,89 @@ int spk_edge_attn_bwd_segments(const spk_seg_gather_args* p, spk_stream_t stream
         return 1;
     }
     return launch_seg_gather(a, (cudaStream_t)stream);
+}
+
+static bool agg_geom_ok(const spk_agg_geom& g, AggGeom* out, const char* who) {
+    if (g.n_heads < 1 || g.n_heads > 2 || g.f_chunks < 1 || g.f_chunks > 15 || g.r_chunks < 1 || g.r_chunks > 15 ||
+        g.lz != 4 * (2 * g.f_chunks + g.r_chunks)) {
+        set_error("%s: bad geometry H=%d f_chunks=%d r_chunks=%d lz=%d", who, g.n_heads, g.f_chunks, g.r_chunks, g.lz);
+        return false;
+    }
+    out->H = g.n_heads; out->Fx4 = g.f_chunks; out->Fr4 = g.r_chunks; out->LZ = g.lz;
+    return true;
+}
+
+int spk_agg_table(const float* X, int64_t ldx, const float* V, float* T, int64_t ldt, int64_t n_rows, int32_t F,
+                  int32_t f_chunks, spk_stream_t stream) {
+    if (F < 1 || F > 60 || f_chunks != (F + 3) / 4 || ldt < 4 * f_chunks + 4 || ldx < F || !aligned16(V)) {
+        set_error("agg_table: needs 1 <= F <= 60, f_chunks = ceil(F/4), ldt >= 4*f_chunks+4, 16-byte aligned V");
+        return 1;
+    }
+    return launch_agg_table(X, ldx, V, T, ldt, n_rows, F, f_chunks, (cudaStream_t)stream);
+}
+
+int spk_agg_fwd(const spk_agg_fwd_args* p, spk_stream_t stream) {
+    AggFwdArgs a;
+    if (!agg_geom_ok(p->geom, &a.g, "agg_fwd")) return 1;
+    const int wx = 4 * a.g.Fx4 + 4, wr = 4 * a.g.Fr4 + 4;
+    if ((p->ldxr & 3) || (p->ldxc & 3) || (p->ldr & 3) || (p->ldz & 3) || p->ldxr < wx || p->ldxc < wx || p->ldr < wr ||
+        p->ldz < (int64_t)a.g.H * a.g.LZ || !aligned16(p->xrow) || !aligned16(p->xcol) || !aligned16(p->rel) || !aligned16(p->z)) {
+        set_error("agg_fwd: tables must be 16-byte aligned with ld %% 4 == 0 and wide enough");
+        return 1;
+    }
+    a.segptr = p->segptr; a.col = p->col; a.t1 = p->t1; a.t2 = p->t2;
+    a.Xrow = p->xrow; a.ldxr = p->ldxr; a.Xcol = p->xcol; a.ldxc = p->ldxc; a.Rt = p->rel; a.ldr = p->ldr;
+    a.mask = p->mask; a.mask_stride = p->mask_stride;
+    a.Z = p->z; a.ldz = p->ldz; a.den = p->den; a.sw = p->sw; a.nanflag = p->nanflag;
+    a.n_rows = p->n_rows; a.alpha = p->alpha;
+    a.hub = hub_of(p->hub);
+    if (a.hub.n_tasks > 0 && (a.hub.ldpart < AGG_LDPART || (a.hub.ldpart & 3) || !aligned16(a.hub.partial))) {
+        set_error("agg_fwd: hub partial buffer needs ldpart >= %d, ldpart %% 4 == 0", AGG_LDPART);
+        return 1;
+    }
+    return launch_agg_fwd(a, (cudaStream_t)stream);
+}
+
+int spk_agg_bwd_pre(const float* out, const float* dout, int64_t ldo, const float* den, int32_t n_heads, int32_t d_head,
+                    int32_t apply_elu, float* dhn, int64_t ldd, float* dden, int64_t n_rows, spk_stream_t stream) {
+    if (n_heads < 1 || d_head < 1 || ldo < (int64_t)n_heads * d_head || ldd < (int64_t)n_heads * d_head) {
+        set_error("agg_bwd_pre: bad shape");
+        return 1;
+    }
+    return launch_agg_bwd_pre(out, dout, ldo, den, n_heads, d_head, apply_elu, dhn, ldd, dden, n_rows, (cudaStream_t)stream);
+}
+
+int spk_agg_bwd_rows(const spk_agg_bwd_args* p, spk_stream_t stream) {
+    AggBwdArgs a;
+    if (!agg_geom_ok(p->geom, &a.g, "agg_bwd_rows")) return 1;
+    const int wx = 4 * a.g.Fx4 + 4, wr = 4 * a.g.Fr4 + 4;
+    if ((p->ldxr & 3) || (p->ldxc & 3) || (p->ldr & 3) || (p->ldz & 3) || (p->ldgx & 3) || (p->ldgr & 3) || (p->ldro & 3) ||
+        p->ldxr < wx || p->ldxc < wx || p->ldr < wr || p->ldz < (int64_t)a.g.H * a.g.LZ ||
+        p->ldgx < (int64_t)a.g.H * 4 * a.g.Fx4 || p->ldgr < (int64_t)a.g.H * 4 * a.g.Fr4 || p->ldro < wx ||
+        !aligned16(p->xrow) || !aligned16(p->xcol) || !aligned16(p->rel) || !aligned16(p->dz) || !aligned16(p->gx) ||
+        !aligned16(p->gr) || !aligned16(p->rowout) || !aligned16(p->rec) || !p->rowsc || !aligned16(p->rowsc)) {
+        set_error("agg_bwd_rows: bad leading dimension or alignment");
+        return 1;
+    }
+    a.segptr = p->segptr; a.col = p->col; a.t1 = p->t1; a.t2 = p->t2;
+    a.Xrow = p->xrow; a.ldxr = p->ldxr; a.Xcol = p->xcol; a.ldxc = p->ldxc; a.Rt = p->rel; a.ldr = p->ldr;
+    a.mask = p->mask; a.mask_stride = p->mask_stride;
+    a.dZ = p->dz; a.ldz = p->ldz; a.den = p->den; a.sw = p->sw; a.dden = p->dden;
+    a.Gx = p->gx; a.ldgx = p->ldgx; a.Gr = p->gr; a.ldgr = p->ldgr; a.rowout = p->rowout; a.ldro = p->ldro; a.rowsc = p->rowsc; a.rec = p->rec;
+    a.n_rows = p->n_rows; a.alpha = p->alpha;
+    a.hub = hub_of(p->hub);
+    if (a.hub.n_tasks > 0 && a.hub.ldpart < 8) { set_error("agg_bwd_rows: hub ldpart must be >= 8"); return 1; }
+    return launch_agg_bwd_rows(a, (cudaStream_t)stream);
+}
+
+int spk_agg_dx(const float* rowout, int64_t ldro, const float* dxc, int64_t ldc, const float* V, int64_t n_rows, int32_t F,
+               int32_t f_chunks, int32_t n_heads, float* dX, int64_t lddx, float* dq, spk_stream_t stream) {
+    if (F < 1 || f_chunks != (F + 3) / 4 || n_heads < 1 || n_heads > 2 || ldro < 4 * f_chunks + 4 ||
+        ldc < (int64_t)n_heads * 4 * f_chunks + n_heads || lddx < F || !aligned16(V) || !aligned16(dq)) {
+        set_error("agg_dx: bad shape or alignment");
+        return 1;
+    }
+    return launch_agg_dx(rowout, ldro, dxc, ldc, V, n_rows, F, f_chunks, n_heads, dX, lddx, dq, (cudaStream_t)stream);
 }
 
 int spk_spmm_rowsum_fwd(const int32_t* segptr, const int32_t* perm, const float* w, int64_t ldw, int32_t width,

@@ -16,7 +16,7 @@ namespace spk {
 int gemm_tc_ldt(int K);
 int gemm_nn_tc_supported(const float* A, long lda, long M, int N, int K);
 int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N, int K,
-               int accumulate, float* workspace, cudaStream_t s);
+               int accumulate, float* workspace, cudaStream_t s, int act = 0);
 int gemm_tn_tc_supported(const float* A, long lda, const float* B, long ldb, long M, int Ka, int Nb);
 long gemm_tn_tc_workspace_floats(long M, int Ka, int Nb);
 int gemm_tn_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int Ka, int Nb,

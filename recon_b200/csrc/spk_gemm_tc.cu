@@ -76,7 +76,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
 
 struct TcParams {
     float* C; long ldc; long M; int N; int K; int BN; int n_tiles_n; int stages; int accumulate; int c_vec;
+    int act;                                    // epilogue: 0 = none, 1 = ELU (GAT/layers.py:175) on the final value
 };
+
+// ELU(x) = x (x > 0) else expm1(x); same evaluation as the edge kernels (degree-5 polynomial near 0)
+__device__ __forceinline__ float tc_elu(float x) {
+    const float big = exp2f(x * 1.4426950408889634f) - 1.0f;
+    const float small = x * (1.0f + x * (0.5f + x * (0.16666667f + x * (0.041666668f + x * 0.0083333338f))));
+    const float neg = x > -0.125f ? small : big;
+    return x > 0.f ? x : neg;
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
@@ -220,12 +229,16 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
                         if (p.c_vec && col + 3 < p.N) {
                             if (p.accumulate) o = f4add(o, *reinterpret_cast<const float4*>(crow + col));
+                            if (p.act) o = make_float4(tc_elu(o.x), tc_elu(o.y), tc_elu(o.z), tc_elu(o.w));
                             *reinterpret_cast<float4*>(crow + col) = o;
                         } else {
                             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                if (col + k < p.N) crow[col + k] = p.accumulate ? crow[col + k] + ov[k] : ov[k];
+                                if (col + k < p.N) {
+                                    const float r1 = p.accumulate ? crow[col + k] + ov[k] : ov[k];
+                                    crow[col + k] = p.act ? tc_elu(r1) : r1;
+                                }
                         }
                     }
                 }
@@ -295,7 +308,7 @@ int gemm_nn_tc_supported(const float* A, long lda, long M, int N, int K) {
 
 // workspace: 2 * N * ldt floats for the split / transposed weights
 int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N, int K,
-               int accumulate, float* workspace, cudaStream_t s) {
+               int accumulate, float* workspace, cudaStream_t s, int act) {
     const int ldt = gemm_tc_ldt(K);
     float* bhi = workspace;
     float* blo = workspace + (long)N * ldt;
@@ -320,7 +333,7 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
 
     TcParams p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.n_tiles_n = n_tiles_n; p.stages = stages;
-    p.accumulate = accumulate;
+    p.accumulate = accumulate; p.act = act;
     p.c_vec = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
     static int smem_set = 0;
     if (smem_set < smem) {

@@ -60,8 +60,9 @@ def extended_weights(a_list, a2_list, in_features, geom):
 
 # ---- dense products --------------------------------------------------------------------------
 
-def gemm_nn(A, B, out=None, accumulate=False):
-    """out[M,N] (+)= A[M,K] @ B[K,N] on the library's GEMM (row-major, last-dim contiguous views allowed)."""
+def gemm_nn(A, B, out=None, accumulate=False, act=0):
+    """out[M,N] (+)= A[M,K] @ B[K,N] on the library's GEMM (row-major, last-dim contiguous views allowed).
+    act=1 applies ELU to the final value (fused into the tensor-core epilogue)."""
     assert A.dim() == 2 and B.dim() == 2 and A.shape[1] == B.shape[0]
     assert A.stride(1) == 1 and B.stride(1) == 1
     M, K = A.shape
@@ -71,20 +72,22 @@ def gemm_nn(A, B, out=None, accumulate=False):
         out = torch.empty(M, N, dtype=torch.float32, device=A.device)
     assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == N
     if M and N:
+        lib = _lib.load()
         if K == 0:
             if not accumulate:
                 out.zero_()
-            return out
-        lib = _lib.load()
-        if USE_TC and M >= TC_MIN_ROWS and N <= 512 and lib.spk_gemm_nn_tc_supported(_lib.ptr(A), A.stride(0), M, N, K):
+        elif USE_TC and M >= TC_MIN_ROWS and N <= 512 and lib.spk_gemm_nn_tc_supported(_lib.ptr(A), A.stride(0), M, N, K):
             # tcgen05 tensor cores, 3xTF32 (fp32-accurate)
             ws = torch.empty(lib.spk_gemm_tc_workspace_floats(N, K), dtype=torch.float32, device=A.device)
-            _lib.check(lib.spk_gemm_nn_tc(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
-                                          out.stride(0), M, N, K, int(accumulate), _lib.ptr(ws), _lib.stream_ptr()),
-                       "gemm_nn_tc")
+            _lib.check(lib.spk_gemm_nn_tc_act(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
+                                              out.stride(0), M, N, K, int(accumulate), int(act), _lib.ptr(ws),
+                                              _lib.stream_ptr()), "gemm_nn_tc")
+            return out
         else:
             _lib.check(lib.spk_gemm_nn(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(out),
                                        out.stride(0), M, N, K, int(accumulate), _lib.stream_ptr()), "gemm_nn")
+        if act:
+            _lib.check(lib.spk_elu_inplace(_lib.ptr(out), out.stride(0), M, N, _lib.stream_ptr()), "elu_inplace")
     return out
 
 
@@ -209,23 +212,25 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
     graph.row_hubs.fill(a.hub, part_a, 2 * MAX_HEADS)
     _lib.check(lib.spk_edge_attn_bwd_rows(C.byref(a), _lib.stream_ptr()), "edge_attn_bwd_rows")
 
-    def seg(ptr, src, pos, hubs, dst, n_seg, tag):
-        s = _lib.SegGatherArgs()
-        s.segptr = ptr.data_ptr(); s.src = src.data_ptr(); s.pos = pos.data_ptr()
-        s.G = G.data_ptr(); s.ldg = ldg; s.rec = rec.data_ptr()
-        s.out = dst.data_ptr(); s.ldout = dst.stride(0); s.n_seg = n_seg
-        s.flags = 1 if (n_seg > 0 and src.numel() < 5 * n_seg) else 0        # many short segments -> streaming kernel
-        s.geom = geom.struct()
-        part = _hub_partial(hubs, geom.Wd, dev)
-        hubs.fill(s.hub, part, geom.Wd)
-        _lib.current_tag = tag
-        try:
-            _lib.check(lib.spk_edge_attn_bwd_segments(C.byref(s), _lib.stream_ptr()), "edge_attn_bwd_segments")
-        finally:
-            _lib.current_tag = ""
+    seg_gather(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, G, ldg, rec, geom, dP2, graph.n_cols, "cols")
+    seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, G, ldg, rec, geom, dP3, graph.n_rel, "rels")
 
-    seg(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, dP2, graph.n_cols, "cols")
-    seg(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, dP3, graph.n_rel, "rels")
+
+def seg_gather(ptr, src, pos, hubs, G, ldg, rec, geom, dst, n_seg, tag):
+    """K4 launch: dst[seg] = [ sum_e w_e,h G[src_e] (per head chunk) | sum_e ds_e,h | 0 ] over the segments of `ptr`."""
+    s = _lib.SegGatherArgs()
+    s.segptr = ptr.data_ptr(); s.src = src.data_ptr(); s.pos = pos.data_ptr()
+    s.G = G.data_ptr(); s.ldg = ldg; s.rec = rec.data_ptr()
+    s.out = dst.data_ptr(); s.ldout = dst.stride(0); s.n_seg = n_seg
+    s.flags = 1 if (n_seg > 0 and src.numel() < 5 * n_seg) else 0        # many short segments -> streaming kernel
+    s.geom = geom.struct()
+    part = _hub_partial(hubs, geom.Wd, G.device)
+    hubs.fill(s.hub, part, geom.Wd)
+    _lib.current_tag = tag
+    try:
+        _lib.check(_lib.load().spk_edge_attn_bwd_segments(C.byref(s), _lib.stream_ptr()), "edge_attn_bwd_segments")
+    finally:
+        _lib.current_tag = ""
 
 
 class AttentionGroupFn(torch.autograd.Function):
@@ -319,11 +324,191 @@ class AttentionGroupFn(torch.autograd.Function):
         return dX, dWn, dRel, dWr, None, None, None, None, None, None
 
 
+# ---- aggregate-then-project variant (input narrower than the projection, i.e. layer 1) ---------
+
+AGG_MODE = "auto"      # "auto": use it where it moves fewer bytes; "off": never; "force": wherever the shape is supported
+AGG_MAX_HEADS = 2
+
+
+class AggGeometry:
+    """Shapes of the aggregate-then-project path (csrc/spk_agg.cuh): table rows [x | pad | 4 scalars | pad]."""
+
+    def __init__(self, n_heads, in_features, nrela_dim, d_head):
+        self.H, self.F, self.Rd, self.D = n_heads, in_features, nrela_dim, d_head
+        self.Fx4, self.Fr4 = (in_features + 3) // 4, (nrela_dim + 3) // 4
+        self.Fp, self.Rp = 4 * self.Fx4, 4 * self.Fr4
+        self.LX = (self.Fp + 4 + 7) // 8 * 8
+        self.LR = (self.Rp + 4 + 7) // 8 * 8
+        self.LZ = 2 * self.Fp + self.Rp
+
+    @staticmethod
+    def supported(n_heads, in_features, nrela_dim):
+        return 1 <= n_heads <= AGG_MAX_HEADS and 1 <= in_features <= 60 and 1 <= nrela_dim <= 60
+
+    def struct(self):
+        return _lib.AggGeom(self.H, self.Fx4, self.Fr4, self.LZ)
+
+
+def use_agg_path(n_heads, in_features, nrela_dim, d_head, graph):
+    if AGG_MODE == "off" or getattr(graph, "dist", None) is not None or graph.n_cols != graph.n_nodes:
+        return False
+    if not AggGeometry.supported(n_heads, in_features, nrela_dim):
+        return False
+    if AGG_MODE == "force":
+        return True
+    g = AggGeometry(n_heads, in_features, nrela_dim, d_head)
+    return g.LX + g.LR < n_heads * d_head          # gathered bytes per edge: input rows vs one projected row
+
+
+def agg_weights(a_list, a2_list, geom):
+    """a_h [D, 2F+Rd], a_2,h [1, D] (GAT/layers.py:100-105) ->
+         Wa [H, LZ, D]  a_h^T with zero rows at the pad positions of Zn_h = [sw x_i | sum w x_j | sum w r_k]
+         V  [F, 4]      (A2^T a_2^T)_0, (..)_1, (A1^T a_2^T)_0, (..)_1      score vectors of X~
+         V3 [Rd, 4]     (A3^T a_2^T)_0, (..)_1, 0, 0                        score vectors of Rel~
+    Differentiable torch ops on these tiny tensors, so autograd chains back to a and a_2."""
+    F, Rd, Fp = geom.F, geom.Rd, geom.Fp
+    a0 = a_list[0]
+    Wa = a0.new_zeros(geom.H, geom.LZ, geom.D)
+    V = a0.new_zeros(F, 4)
+    V3 = a0.new_zeros(Rd, 4)
+    for h, (a, a2) in enumerate(zip(a_list, a2_list)):
+        at = a.t()                                        # [2F+Rd, D]
+        qa = at.mm(a2.t()).squeeze(1)                     # a^T a_2^T
+        Wa[h, :F] = at[:F]
+        Wa[h, Fp:Fp + F] = at[F:2 * F]
+        Wa[h, 2 * Fp:2 * Fp + Rd] = at[2 * F:]
+        V[:, 2 + h] = qa[:F]
+        V[:, h] = qa[F:2 * F]
+        V3[:, h] = qa[2 * F:]
+    return Wa, V, V3
+
+
+def _agg_table(X, V, ld, chunks):
+    T = torch.empty(X.shape[0], ld, dtype=torch.float32, device=X.device)
+    if X.shape[0]:
+        _lib.check(_lib.load().spk_agg_table(_lib.ptr(X), X.stride(0), _lib.ptr(V), _lib.ptr(T), ld, X.shape[0],
+                                             X.shape[1], chunks, _lib.stream_ptr()), "agg_table")
+    return T
+
+
+class AggGroupFn(torch.autograd.Function):
+    """One layer group on the aggregate-then-project kernels: (X, Rel, Wa, V, V3) -> ELU?(attention output) [N, H*D].
+    Same math as AttentionGroupFn (GAT/layers.py:124-175), re-associated so the edges gather input rows."""
+
+    @staticmethod
+    def forward(ctx, X, Rel, Wa, V, V3, graph, geom, alpha, apply_elu, mask_csr, nanflag):
+        lib = _lib.load()
+        X = X.contiguous(); Rel = Rel.contiguous(); Wa = Wa.contiguous(); V = V.contiguous(); V3 = V3.contiguous()
+        n, dev = graph.n_nodes, X.device
+        H, D, LZ = geom.H, geom.D, geom.LZ
+        Xt = _agg_table(X, V, geom.LX, geom.Fx4)
+        Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
+        Z = torch.empty(n, H * LZ, dtype=torch.float32, device=dev)
+        den = torch.empty(n, H, dtype=torch.float32, device=dev)
+        sw = torch.empty(n, H, dtype=torch.float32, device=dev)
+        a = _lib.AggFwdArgs()
+        a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
+        a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
+        a.xrow = Xt.data_ptr(); a.ldxr = Xt.stride(0); a.xcol = Xt.data_ptr(); a.ldxc = Xt.stride(0)
+        a.rel = Rt.data_ptr(); a.ldr = Rt.stride(0)
+        if mask_csr is not None:
+            a.mask = mask_csr.data_ptr(); a.mask_stride = mask_csr.stride(0)
+        a.z = Z.data_ptr(); a.ldz = Z.stride(0); a.den = den.data_ptr(); a.sw = sw.data_ptr()
+        a.nanflag = nanflag.data_ptr(); a.n_rows = n; a.alpha = float(alpha); a.geom = geom.struct()
+        partial = _hub_partial(graph.row_hubs, 264, dev)
+        graph.row_hubs.fill(a.hub, partial, 264)
+        _lib.check(lib.spk_agg_fwd(C.byref(a), _lib.stream_ptr()), "agg_fwd")
+        out = torch.empty(n, H * D, dtype=torch.float32, device=dev)
+        for h in range(H):                                  # a.mm(.) of layers.py:137 on the aggregated rows (+ ELU 175)
+            gemm_nn(Z[:, h * LZ:(h + 1) * LZ], Wa[h], out=out[:, h * D:(h + 1) * D], act=int(apply_elu))
+        ctx.save_for_backward(X, Rel, Wa, V, V3, Xt, Rt, Z, out, den, sw)
+        ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr = graph, geom, alpha, apply_elu, mask_csr
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = _lib.load()
+        geom, graph = ctx.geom, ctx.graph
+        X, Rel, Wa, V, V3, Xt, Rt, Z, out, den, sw = ctx.saved_tensors
+        graph.build_backward()
+        n, dev = graph.n_nodes, X.device
+        H, D, LZ, Fp, Rp = geom.H, geom.D, geom.LZ, geom.Fp, geom.Rp
+        f32 = dict(dtype=torch.float32, device=dev)
+        dout = dout.contiguous()
+        dhn = torch.empty(n, H * D, **f32)
+        dden = torch.empty(n, H, **f32)
+        _lib.check(lib.spk_agg_bwd_pre(_lib.ptr(out), _lib.ptr(dout), out.stride(0), _lib.ptr(den), H, D,
+                                       int(ctx.apply_elu), _lib.ptr(dhn), dhn.stride(0), _lib.ptr(dden), n,
+                                       _lib.stream_ptr()), "agg_bwd_pre")
+        dZ = torch.empty(n, H * LZ, **f32)
+        dWa = torch.empty_like(Wa)
+        for h in range(H):
+            dh = dhn[:, h * D:(h + 1) * D]
+            gemm_nn(dh, Wa[h].t().contiguous(), out=dZ[:, h * LZ:(h + 1) * LZ])
+            gemm_tn(Z[:, h * LZ:(h + 1) * LZ], dh, out=dWa[h])
+        Gx = torch.empty(n, H * Fp, **f32)
+        Gr = torch.empty(n, H * Rp, **f32)
+        rowout = torch.empty(n, Fp + 4, **f32)
+        rec = torch.empty(max(1, graph.n_edges), 2 * H, **f32)
+        a = _lib.AggBwdArgs()
+        a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
+        a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
+        a.xrow = Xt.data_ptr(); a.ldxr = Xt.stride(0); a.xcol = Xt.data_ptr(); a.ldxc = Xt.stride(0)
+        a.rel = Rt.data_ptr(); a.ldr = Rt.stride(0)
+        if ctx.mask_csr is not None:
+            a.mask = ctx.mask_csr.data_ptr(); a.mask_stride = ctx.mask_csr.stride(0)
+        a.dz = dZ.data_ptr(); a.ldz = dZ.stride(0)
+        a.den = den.data_ptr(); a.sw = sw.data_ptr(); a.dden = dden.data_ptr()
+        a.gx = Gx.data_ptr(); a.ldgx = Gx.stride(0); a.gr = Gr.data_ptr(); a.ldgr = Gr.stride(0)
+        rowsc = torch.empty(n, 8, **f32)
+        a.rowout = rowout.data_ptr(); a.ldro = rowout.stride(0); a.rowsc = rowsc.data_ptr(); a.rec = rec.data_ptr()
+        a.n_rows = n; a.alpha = float(ctx.alpha); a.geom = geom.struct()
+        part = _hub_partial(graph.row_hubs, 8, dev)
+        graph.row_hubs.fill(a.hub, part, 8)
+        _lib.check(lib.spk_agg_bwd_rows(C.byref(a), _lib.stream_ptr()), "agg_bwd_rows")
+        del dZ
+        # column pass: dX through the gathered side, per head chunk; relation pass: dRel
+        gx_geom, gr_geom = Geometry(H, Fp), Geometry(H, Rp)
+        dXc = torch.empty(graph.n_cols, gx_geom.Wd, **f32)
+        seg_gather(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, Gx, Gx.stride(0), rec, gx_geom, dXc,
+                   graph.n_cols, "cols")
+        dRc = torch.empty(graph.n_rel, gr_geom.Wd, **f32)
+        seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, Gr, Gr.stride(0), rec, gr_geom, dRc,
+                   graph.n_rel, "rels")
+        dX = torch.empty(n, geom.F, **f32)
+        dq = torch.empty(n, 4, **f32)
+        _lib.check(lib.spk_agg_dx(_lib.ptr(rowout), rowout.stride(0), _lib.ptr(dXc), dXc.stride(0), _lib.ptr(V), n,
+                                  geom.F, geom.Fx4, H, _lib.ptr(dX), dX.stride(0), _lib.ptr(dq), _lib.stream_ptr()),
+                   "agg_dx")
+        dV = gemm_tn(X, dq) if ctx.needs_input_grad[3] else None
+        dq3 = dRc[:, H * Rp:H * Rp + H].contiguous()                      # [R, H]
+        dRel = None
+        if ctx.needs_input_grad[1]:
+            dRel = dRc[:, :geom.Rd].clone()
+            for h in range(1, H):
+                dRel += dRc[:, h * Rp:h * Rp + geom.Rd]
+            dRel = gemm_nn(dq3, V3[:, :H].t().contiguous(), out=dRel, accumulate=True)
+        dV3 = None
+        if ctx.needs_input_grad[4]:
+            dV3 = torch.zeros_like(V3)
+            dV3[:, :H] = gemm_tn(Rel, dq3)
+        return dX, dRel, dWa, dV, dV3, None, None, None, None, None, None
+
+
 def attention_group(X, Rel, a_list, a2_list, graph, alpha, apply_elu, mask_csr, nanflag):
     """All heads of one layer (looping over groups of <=4): returns [N, sum_h D]."""
     outs = []
     F = X.shape[1]
     D = a_list[0].shape[0]
+    Rd = a_list[0].shape[1] - 2 * F
+    if use_agg_path(min(len(a_list), AGG_MAX_HEADS), F, Rd, D, graph):
+        for g0 in range(0, len(a_list), AGG_MAX_HEADS):
+            al, a2l = a_list[g0:g0 + AGG_MAX_HEADS], a2_list[g0:g0 + AGG_MAX_HEADS]
+            geom = AggGeometry(len(al), F, Rd, D)
+            Wa, V, V3 = agg_weights(al, a2l, geom)
+            m = None if mask_csr is None else mask_csr[g0:g0 + AGG_MAX_HEADS].contiguous()
+            outs.append(AggGroupFn.apply(X, Rel, Wa, V, V3, graph, geom, alpha, apply_elu, m, nanflag))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
     for g0 in range(0, len(a_list), MAX_HEADS):
         al, a2l = a_list[g0:g0 + MAX_HEADS], a2_list[g0:g0 + MAX_HEADS]
         geom = Geometry(len(al), D)

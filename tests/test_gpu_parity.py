@@ -186,8 +186,19 @@ def test_special_spmm_golden(name):
     assert np.array_equal(w.grad.cpu().numpy(), g["grad_w"])
 
 
+@pytest.fixture(params=["auto", "force", "off"])
+def agg_path(request):
+    """Layer groups run on the project-then-gather kernels (K2/K3), on the aggregate-then-project kernels (K2'/K3',
+    input-narrow layers) or, with "auto", on whichever moves fewer bytes; every model test is run on all three."""
+    from recon_b200 import functional as SF
+    old = SF.AGG_MODE
+    SF.AGG_MODE = request.param
+    yield request.param
+    SF.AGG_MODE = old
+
+
 @pytest.mark.parametrize("name", ["layer_concat", "layer_noconcat_nhop"])
-def test_attention_layer_golden(name):
+def test_attention_layer_golden(name, agg_path):
     from recon_b200 import SpGraphAttentionLayer
     g = load_golden(name)
     n, f = g["x"].shape
@@ -213,7 +224,7 @@ def test_attention_layer_golden(name):
 
 # ---- full model against the reference's own outputs ---------------------------------------------------
 @pytest.mark.parametrize("name", MODEL_CASES)
-def test_model_golden(name):
+def test_model_golden(name, agg_path):
     g = load_golden(name)
     model = build_model(g, float(g["p_drop"]))
     masks = golden_masks(g)
@@ -258,7 +269,7 @@ def test_state_dict_keys_match_reference():
 
 # ---- seeded synthetic inputs against the oracle (C1 shape, uniform and Zipf with hub rows) ------------
 @pytest.mark.parametrize("alpha,n_nhop,p_drop", [(None, 0, 0.0), (1.1, 0, 0.0), (1.1, 20000, 0.3)])
-def test_model_vs_oracle_c1(alpha, n_nhop, p_drop):
+def test_model_vs_oracle_c1(alpha, n_nhop, p_drop, agg_path):
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
     from oracle import ref_torch as O
@@ -293,7 +304,7 @@ def test_model_vs_oracle_c1(alpha, n_nhop, p_drop):
         assert model.prepare_graph((edge, etype), nhop).row_hubs.n_hubs > 0      # the hub path was exercised
 
 
-def test_run_to_run_bit_identical():
+def test_run_to_run_bit_identical(agg_path):
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
     from oracle import ref_torch as O
@@ -313,7 +324,7 @@ def test_run_to_run_bit_identical():
         assert torch.equal(a, b)
 
 
-def test_overflow_raises_assertion_like_reference():
+def test_overflow_raises_assertion_like_reference(agg_path):
     """exp without max-subtraction (GAT/layers.py:143-146): huge scores overflow to inf -> NaN -> AssertionError."""
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
@@ -330,7 +341,7 @@ def test_overflow_raises_assertion_like_reference():
         model(None, torch.arange(n), (edge, etype), nhop)
 
 
-def test_training_mode_dropout_runs_and_is_unbiased_in_shape():
+def test_training_mode_dropout_runs_and_is_unbiased_in_shape(agg_path):
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
     from oracle import ref_torch as O
