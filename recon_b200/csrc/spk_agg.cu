@@ -718,6 +718,58 @@ int launch_agg_bwd_t(const AggBwdArgs& a, cudaStream_t s) {
 // ---- row-wise helpers ------------------------------------------------------------------------------
 // dhn = dOut * ELU'(hn) from the saved output (hn > 0: out = hn; else out = e^hn - 1, ELU' = out + 1, hn = log1p(out));
 // dden_h = -(dhn_h . hn_h) / den_h
+// log1p(x) on (-1, 0] as log(u) * x / (u - 1), u = fl(1 + x): the rounding of u cancels to first order (|rel err| ~ 2e-7)
+__device__ __forceinline__ float fast_log1p(float x) {
+    const float u = 1.0f + x;
+    const float d = u - 1.0f;
+    return d == 0.f ? x : __logf(u) * __fdividef(x, d);
+}
+
+__device__ __forceinline__ void bwd_pre_elem(float ov, float gv, int apply_elu, float& dh, float& p) {
+    float hv = ov;
+    dh = gv;
+    if (apply_elu) {
+        const bool pos = ov > 0.f;
+        dh = pos ? gv : gv * (ov + 1.f);
+        hv = pos ? ov : (ov > -1.f ? fast_log1p(ov) : 0.f);
+    }
+    p = fmaf(dh, hv, p);
+}
+
+// vector path: D % 4 == 0, 16-byte aligned rows, H <= 4; one warp per row, a lane owns float4 chunks c4 = lane + 32 k of the
+// H*D-wide row (a chunk never straddles a head), the per-head dots are reduced with one butterfly per head
+__global__ void __launch_bounds__(256)
+agg_bwd_pre_vec_kernel(const float* __restrict__ out, const float* __restrict__ dout, long ldo, const float* __restrict__ den,
+                       int H, int D4, int apply_elu, float* __restrict__ dhn, long ldd, float* __restrict__ dden, long n) {
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float* o = out + row * ldo;
+    const float* g = dout + row * ldo;
+    float* d = dhn + row * ldd;
+    const int n4 = H * D4;
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c4 = lane; c4 < n4; c4 += 32) {
+        const float4 ov = ldg4_stream(o + c4 * 4), gv = ldg4_stream(g + c4 * 4);
+        float4 dh;
+        float acc = 0.f;
+        bwd_pre_elem(ov.x, gv.x, apply_elu, dh.x, acc);
+        bwd_pre_elem(ov.y, gv.y, apply_elu, dh.y, acc);
+        bwd_pre_elem(ov.z, gv.z, apply_elu, dh.z, acc);
+        bwd_pre_elem(ov.w, gv.w, apply_elu, dh.w, acc);
+        st4(d + c4 * 4, dh);
+        const int h = c4 / D4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) p[k] += (h == k) ? acc : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k >= H) break;
+        const float t = warp_sum(p[k]);
+        if (lane == 0) dden[row * H + k] = -t / __ldg(den + row * H + k);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 agg_bwd_pre_kernel(const float* __restrict__ out, const float* __restrict__ dout, long ldo, const float* __restrict__ den,
                    int H, int D, int apply_elu, float* __restrict__ dhn, long ldd, float* __restrict__ dden, long n) {
@@ -730,15 +782,9 @@ agg_bwd_pre_kernel(const float* __restrict__ out, const float* __restrict__ dout
     for (int h = 0; h < H; ++h) {
         float p = 0.f;
         for (int c = lane; c < D; c += 32) {
-            const float ov = __ldg(o + h * D + c), gv = __ldg(g + h * D + c);
-            float dh = gv, hv = ov;
-            if (apply_elu) {
-                const bool pos = ov > 0.f;
-                dh = pos ? gv : gv * (ov + 1.f);
-                hv = pos ? ov : (ov > -1.f ? log1pf(ov) : 0.f);
-            }
+            float dh;
+            bwd_pre_elem(__ldg(o + h * D + c), __ldg(g + h * D + c), apply_elu, dh, p);
             d[h * D + c] = dh;
-            p = fmaf(dh, hv, p);
         }
         p = warp_sum(p);
         if (lane == 0) dden[row * H + h] = -p / __ldg(den + row * H + h);
@@ -808,7 +854,12 @@ int launch_agg_bwd_rows(const AggBwdArgs& a, cudaStream_t s) {
 int launch_agg_bwd_pre(const float* out, const float* dout, long ldo, const float* den, int H, int D, int apply_elu,
                        float* dhn, long ldd, float* dden, long n, cudaStream_t s) {
     if (n <= 0) return 0;
-    agg_bwd_pre_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(out, dout, ldo, den, H, D, apply_elu, dhn, ldd, dden, n);
+    const bool vec = (D % 4 == 0) && H <= 4 && (ldo % 4 == 0) && (ldd % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dhn)) & 15) == 0;
+    if (vec)
+        agg_bwd_pre_vec_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(out, dout, ldo, den, H, D / 4, apply_elu, dhn, ldd, dden, n);
+    else
+        agg_bwd_pre_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(out, dout, ldo, den, H, D, apply_elu, dhn, ldd, dden, n);
     return check_launch("agg_bwd_pre");
 }
 

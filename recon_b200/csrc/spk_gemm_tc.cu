@@ -77,6 +77,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
 struct TcParams {
     float* C; long ldc; long M; int N; int K; int BN; int n_tiles_n; int stages; int accumulate; int c_vec;
     int act;                                    // epilogue: 0 = none, 1 = ELU (GAT/layers.py:175) on the final value
+    int c_tma;                                  // epilogue stores through shared memory + TMA (coalesced 128 B rows)
 };
 
 // ELU(x) = x (x > 0) else expm1(x); same evaluation as the edge kernels (degree-5 polynomial near 0)
@@ -89,7 +90,7 @@ __device__ __forceinline__ float tc_elu(float x) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                  const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 4];
     __shared__ uint32_t tmem_slot;
@@ -202,7 +203,66 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 mbar_arrive(conv(s));
             }
         }
-    } else {                                                       // ---- epilogue (warps 6..9)
+    } else if (p.c_tma) {                                          // ---- epilogue (warps 6..9), coalesced
+        // Each warp owns the 32 accumulator rows of its TMEM lane quarter. A 32-column chunk is read with one
+        // tcgen05.ld (a lane = one row), written to a 128B-swizzled [32 x 32] staging tile in shared memory and
+        // stored (or reduce-added, for C +=) by TMA: full 128 B row segments, clipped at the M / N edges.
+        const int q = warp & 3;
+        const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes + (uint32_t)q * 8192u;
+        uint32_t tl = 0, sb = 0;
+        for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+            const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+            const int row0 = (int)(tile / p.n_tiles_n) * TC_BM + q * 32;
+            const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
+            mbar_wait(tfull(acc), aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.act) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(tc_elu(__uint_as_float(r[j])));
+                }
+                // the store issued two chunks ago read this staging buffer: wait until at most one store is still reading
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t stg = stg0 + sb * 4096u;
+                const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t a = rowaddr + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                                 "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (p.accumulate)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmC), "r"(n0 + c0), "r"(row0), "r"(stg) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmC), "r"(n0 + c0), "r"(row0), "r"(stg) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                sb ^= 1u;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {                                                       // ---- epilogue (warps 6..9), per-thread rows (unaligned C)
         const int q = warp & 3;                                    // TMEM lane quarter this warp may access
         uint32_t tl = 0;
         for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
@@ -317,24 +377,32 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     if (int rc = check_launch("tc_prepare_b")) return rc;
 
     const int n_tiles_n = (N + 255) / 256;
-    int BN = ((N + n_tiles_n - 1) / n_tiles_n + 15) / 16 * 16;
+    // one N tile: multiple of 16 columns (UMMA N); several: multiple of 32 so that the 32-column store boxes of the
+    // epilogue never reach into the neighbouring tile
+    const int bn_round = n_tiles_n > 1 ? 32 : 16;
+    int BN = ((N + n_tiles_n - 1) / n_tiles_n + bn_round - 1) / bn_round * bn_round;
     if (BN < 16) BN = 16;
     const int b_tile = BN * 128;
     const int stage_bytes = 2 * TC_A_TILE + 2 * b_tile;
-    int stages = (225 * 1024 - 1024) / stage_bytes;
+    const int c_vec = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const int c_tma = c_vec && !(act && accumulate);
+    const int staging = c_tma ? 4 * 8192 : 0;                       // 4 epilogue warps x 2 x [32 x 32] fp32
+    int stages = (225 * 1024 - 1024 - staging) / stage_bytes;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     if (stages < 1) { set_error("gemm_tc: tile does not fit shared memory"); return 3; }
-    const int smem = stages * stage_bytes + 1024;
+    const int smem = stages * stage_bytes + staging + 1024;
 
-    CUtensorMap tmA, tmBhi, tmBlo;
+    CUtensorMap tmA, tmBhi, tmBlo, tmC;
     if (int rc = make_map(&tmA, A, M, K, lda, TC_BM)) return rc;
     if (int rc = make_map(&tmBhi, bhi, N, K, ldt, BN)) return rc;
     if (int rc = make_map(&tmBlo, blo, N, K, ldt, BN)) return rc;
+    if (c_tma) { if (int rc = make_map(&tmC, C, M, N, ldc, 32)) return rc; }
+    else tmC = tmA;
 
     TcParams p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.n_tiles_n = n_tiles_n; p.stages = stages;
     p.accumulate = accumulate; p.act = act;
-    p.c_vec = (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    p.c_vec = c_vec; p.c_tma = c_tma;
     static int smem_set = 0;
     if (smem_set < smem) {
         if (cudaFuncSetAttribute(gemm_nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
@@ -349,7 +417,7 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long total = ((M + TC_BM - 1) / TC_BM) * n_tiles_n;
     const unsigned grid = (unsigned)(total < sms ? total : sms);
-    gemm_nn_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmBhi, tmBlo, p);
+    gemm_nn_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmBhi, tmBlo, tmC, p);
     return check_launch("gemm_nn_tc");
 }
 

@@ -69,10 +69,13 @@ def gemm_nn(A, B, out=None, accumulate=False, act=0):
     N = B.shape[1]
     if out is None:
         assert not accumulate
-        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+        # row stride padded to 16 B so the epilogue can store whole 128 B row segments by TMA
+        out = torch.empty(M, (N + 3) // 4 * 4, dtype=torch.float32, device=A.device)[:, :N]
     assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == N
     if M and N:
         lib = _lib.load()
+        if lib.timing is not None:
+            _lib.current_tag = f"{M}x{K}x{N}"
         if K == 0:
             if not accumulate:
                 out.zero_()
@@ -102,6 +105,8 @@ def gemm_tn(A, B, out=None, accumulate=False):
         assert not accumulate
         out = torch.empty(Ka, Nb, dtype=torch.float32, device=A.device)
     if Ka and Nb:
+        if lib.timing is not None:
+            _lib.current_tag = f"{M}x{Ka}x{Nb}"
         if USE_TC and M >= TC_MIN_ROWS and lib.spk_gemm_tn_tc_supported(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0),
                                                                         M, Ka, Nb):
             ws = torch.empty(max(1, lib.spk_gemm_tn_tc_workspace_floats(M, Ka, Nb)), dtype=torch.float32, device=A.device)
