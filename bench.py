@@ -310,7 +310,12 @@ class SingleGPU:
             "edge_attn_bwd_rows": e * (4 * dt + 8 + 8 * h_avg) + 4 * self.e2 + n * (20 * dt),
             "edge_attn_bwd_segments:cols": e * (4 * dt + 8 + 8 * h_avg) + n * (4 * dt),
         }
-        cand = {k: v for k, v in prof.items() if k in algs}
+        cand = {}
+        for k, v in prof.items():                  # per-width tags (":w208") of the segment passes fold into one entry
+            base = k.rsplit(":w", 1)[0]
+            if base in algs:
+                ms0, c0 = cand.get(base, (0.0, 0))
+                cand[base] = (ms0 + v[0], c0 + v[1])
         if not cand:
             return None
         top = max(cand, key=lambda k: cand[k][0])

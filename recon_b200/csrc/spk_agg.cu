@@ -51,6 +51,42 @@ agg_table_kernel(const float* __restrict__ X, long ldx, const float* __restrict_
     }
 }
 
+// even F <= 64, 8-byte aligned rows, ldt <= 128: a lane produces float2 columns (2 lane, 2 lane + 1) and (+64) of the table
+// row; a warp handles AT_R consecutive rows with all row loads issued up front
+constexpr int AT_R = 4;
+__global__ void __launch_bounds__(256)
+agg_table_vec2_kernel(const float* __restrict__ X, long ldx, const float* __restrict__ V, float* __restrict__ T, long ldt,
+                      long n, int F, int F4) {
+    const int lane = threadIdx.x & 31;
+    const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * AT_R;
+    const int f = 2 * lane;
+    float2 xv[AT_R];
+#pragma unroll
+    for (int r = 0; r < AT_R; ++r)
+        xv[r] = (row0 + r < n && f < F) ? reinterpret_cast<const float2*>(X + (row0 + r) * ldx)[lane] : make_float2(0.f, 0.f);
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (f < F) { v0 = ldg4(V + f * 4); v1 = ldg4(V + f * 4 + 4); }
+    const int qoff = 4 * F4, l2 = (int)(ldt >> 1);
+#pragma unroll
+    for (int r = 0; r < AT_R; ++r) {
+        if (row0 + r >= n) break;
+        float q[4];
+        q[0] = warp_sum(fmaf(xv[r].x, v0.x, xv[r].y * v1.x)); q[1] = warp_sum(fmaf(xv[r].x, v0.y, xv[r].y * v1.y));
+        q[2] = warp_sum(fmaf(xv[r].x, v0.z, xv[r].y * v1.z)); q[3] = warp_sum(fmaf(xv[r].x, v0.w, xv[r].y * v1.w));
+        float2* t = reinterpret_cast<float2*>(T + (row0 + r) * ldt);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int c2 = lane + 32 * k, c = 2 * c2;
+            if (c2 >= l2) break;
+            float2 o = make_float2(0.f, 0.f);
+            if (c < F) o = xv[r];
+            else if (c == qoff) o = make_float2(q[0], q[1]);
+            else if (c == qoff + 2) o = make_float2(q[2], q[3]);
+            t[c2] = o;
+        }
+    }
+}
+
 // ---- shared pieces of the streaming edge kernels ---------------------------------------------------
 // A warp owns 32 consecutive aggregation rows (or one hub task); their edges form one stream n = 0..T-1 (spk_stream.cuh).
 // Three index batches of 32 stream positions are in flight: `cur` (scores, exp, weights ready), `b1` (indices loaded,
@@ -353,14 +389,14 @@ agg_fwd_stream_kernel(const AggFwdArgs a) {
 
 // one CTA per hub row: partials added in the fixed order of cta_sum_partials, then the row epilogue
 template <int HT>
-__global__ void __launch_bounds__(SPK_CTA_THREADS)
+__global__ void __launch_bounds__(1024)
 agg_fwd_hub_finalize_kernel(const AggFwdArgs a) {
-    __shared__ __align__(16) float red[SPK_WARPS_PER_CTA][AGG_LDPART];
+    __shared__ __align__(16) float red[32][AGG_LDPART];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int hub = blockIdx.x;
     const int row = __ldg(a.hub.hub_seg + hub);
     const int t0 = __ldg(a.hub.hub_task_ptr + hub), t1 = __ldg(a.hub.hub_task_ptr + hub + 1);
-    cta_sum_partials<(AGG_LDPART + 31) / 32>(a.hub.partial, a.hub.ldpart, t0, t1, AGG_LDPART, &red[0][0], AGG_LDPART);
+    cta_sum_partials<(AGG_LDPART + 31) / 32, 32>(a.hub.partial, a.hub.ldpart, t0, t1, AGG_LDPART, &red[0][0], AGG_LDPART);
     if (wid != 0) return;
     AggAcc<HT> st;
 #pragma unroll
@@ -399,7 +435,7 @@ int launch_agg_fwd_t(const AggFwdArgs& a, cudaStream_t s) {
         const unsigned grid = (a.hub.n_tasks + AGS_WARPS - 1) / AGS_WARPS;
         agg_fwd_stream_kernel<HT, HAS2, true><<<grid, AGS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("agg_fwd_stream_tasks")) return rc;
-        agg_fwd_hub_finalize_kernel<HT><<<a.hub.n_hubs, SPK_CTA_THREADS, 0, s>>>(a);
+        agg_fwd_hub_finalize_kernel<HT><<<a.hub.n_hubs, 1024, 0, s>>>(a);
         if (int rc = check_launch("agg_fwd_hub_finalize")) return rc;
     }
     return 0;
@@ -420,24 +456,37 @@ agg_bwd_ctx_kernel(const AggBwdArgs a) {
     const int sub = lane & 15;
     const bool isx = lane < 16;
     const bool active = sub < (isx ? a.g.Fx4 : a.g.Fr4);
+    const int H = a.g.H;
+    // every load of the row is issued before the first use (one DRAM round trip per row)
     const float4 xs = ldg4(a.Xrow + (long)row * a.ldxr + a.g.Fx4 * 4);
     float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < a.g.Fx4) xi = ldg4(a.Xrow + (long)row * a.ldxr + lane * 4);
-    float4 dxr = make_float4(0.f, 0.f, 0.f, 0.f);
-    float c[2] = {0.f, 0.f}, dd[2] = {0.f, 0.f};
+    float4 ya[2], yy[2];
+    float den[2] = {1.f, 1.f}, swh[2] = {0.f, 0.f}, dd[2] = {0.f, 0.f};
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        if (h >= a.g.H) break;
-        const float rd = 1.0f / __ldg(a.den + (long)row * a.g.H + h);
-        const float swh = __ldg(a.sw + (long)row * a.g.H + h);
-        dd[h] = __ldg(a.dden + (long)row * a.g.H + h);
-        const float* dz = a.dZ + (long)row * a.ldz + (long)h * a.g.LZ;
-        float4 ya = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < a.g.Fx4) ya = f4scale(ldg4_stream(dz + lane * 4), rd);
-        c[h] = warp_sum(f4dot(ya, xi));
-        f4fma(dxr, swh, ya);
+        ya[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+        yy[h] = ya[h];
+        if (h < H) {
+            const float* dz = a.dZ + (long)row * a.ldz + (long)h * a.g.LZ;
+            den[h] = __ldg(a.den + (long)row * H + h);
+            swh[h] = __ldg(a.sw + (long)row * H + h);
+            dd[h] = __ldg(a.dden + (long)row * H + h);
+            if (lane < a.g.Fx4) ya[h] = ldg4(dz + lane * 4);
+            if (active) yy[h] = ldg4(dz + (isx ? 4 : 8) * a.g.Fx4 + sub * 4);
+        }
+    }
+    float4 dxr = make_float4(0.f, 0.f, 0.f, 0.f);
+    float c[2] = {0.f, 0.f};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (h >= H) break;
+        const float rd = 1.0f / den[h];
+        const float4 y0 = f4scale(ya[h], rd);
+        c[h] = warp_sum(f4dot(y0, xi));
+        f4fma(dxr, swh[h], y0);
         if (active) {
-            const float4 y = f4scale(ldg4_stream(dz + (isx ? 4 : 8) * a.g.Fx4 + sub * 4), rd);
+            const float4 y = f4scale(yy[h], rd);
             if (isx) st4(a.Gx + (long)row * a.ldgx + (long)h * 4 * a.g.Fx4 + sub * 4, y);
             else st4(a.Gr + (long)row * a.ldgr + (long)h * 4 * a.g.Fr4 + sub * 4, y);
         }
@@ -792,27 +841,45 @@ agg_bwd_pre_kernel(const float* __restrict__ out, const float* __restrict__ dout
 }
 
 // dX[i,f] = rowout[i,f] + sum_h dxc[i, h*4F4 + f] + sum_c dq[i,c] V[f,c],  dq[i] = (dq2_0, dq2_1, dq1_0, dq1_1)
+// a warp handles DX_R consecutive rows (F <= 64: lane f and f + 32); every load is issued before the first use
+constexpr int DX_R = 2;
 __global__ void __launch_bounds__(256)
 agg_dx_kernel(const float* __restrict__ rowout, long ldro, const float* __restrict__ dxc, long ldc,
               const float* __restrict__ V, long n, int F, int F4, int H, float* __restrict__ dX, long lddx,
               float* __restrict__ dq) {
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * F) return;
-    const long i = idx / F;
-    const int f = (int)(idx - i * F);
-    const float* ro = rowout + i * ldro;
-    const float* xc = dxc + i * ldc;
-    float q[4] = {0.f, 0.f, 0.f, 0.f};
-    float val = __ldg(ro + f);
-    for (int h = 0; h < H; ++h) {
-        val += __ldg(xc + h * 4 * F4 + f);
-        q[h] = __ldg(xc + H * 4 * F4 + h);
-        q[2 + h] = __ldg(ro + 4 * F4 + h);
+    const int lane = threadIdx.x & 31;
+    const long i0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * DX_R;
+    float q[DX_R][4], r0[DX_R][2], c0[DX_R][2], c1[DX_R][2];
+    float4 v[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) v[k] = (lane + 32 * k < F) ? ldg4(V + (lane + 32 * k) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < DX_R; ++r) {
+        const long i = i0 + r < n ? i0 + r : n - 1;
+        const float* ro = rowout + i * ldro;
+        const float* xc = dxc + i * ldc;
+        q[r][0] = __ldg(xc + H * 4 * F4); q[r][1] = H > 1 ? __ldg(xc + H * 4 * F4 + 1) : 0.f;
+        q[r][2] = __ldg(ro + 4 * F4); q[r][3] = H > 1 ? __ldg(ro + 4 * F4 + 1) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int f = lane + 32 * k;
+            r0[r][k] = f < F ? __ldg(ro + f) : 0.f;
+            c0[r][k] = f < F ? __ldg(xc + f) : 0.f;
+            c1[r][k] = (f < F && H > 1) ? __ldg(xc + 4 * F4 + f) : 0.f;
+        }
     }
-    const float4 v = ldg4(V + f * 4);
-    val = fmaf(q[0], v.x, fmaf(q[1], v.y, fmaf(q[2], v.z, fmaf(q[3], v.w, val))));
-    dX[i * lddx + f] = val;
-    if (f == 0) st4(dq + i * 4, make_float4(q[0], q[1], q[2], q[3]));
+#pragma unroll
+    for (int r = 0; r < DX_R; ++r) {
+        const long i = i0 + r;
+        if (i >= n) break;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int f = lane + 32 * k;
+            const float val = fmaf(q[r][0], v[k].x, fmaf(q[r][1], v[k].y, fmaf(q[r][2], v[k].z, fmaf(q[r][3], v[k].w, r0[r][k] + c0[r][k] + c1[r][k]))));
+            if (f < F) dX[i * lddx + f] = val;
+        }
+        if (lane == 0) st4(dq + i * 4, make_float4(q[r][0], q[r][1], q[r][2], q[r][3]));
+    }
 }
 
 __device__ __forceinline__ float elu_exact(float x) {
@@ -835,7 +902,11 @@ elu_inplace_kernel(float* __restrict__ x, long ld, long n, int width) {
 
 int launch_agg_table(const float* X, long ldx, const float* V, float* T, long ldt, long n, int F, int F4, cudaStream_t s) {
     if (n <= 0) return 0;
-    agg_table_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, ldx, V, T, ldt, n, F, F4);
+    const bool vec2 = (F % 2 == 0) && F <= 64 && (ldx % 2 == 0) && (ldt % 2 == 0) && ldt <= 128 &&
+                      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(T)) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(V) & 15) == 0;
+    if (vec2) agg_table_vec2_kernel<<<(unsigned)((n + 8 * AT_R - 1) / (8 * AT_R)), 256, 0, s>>>(X, ldx, V, T, ldt, n, F, F4);
+    else agg_table_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(X, ldx, V, T, ldt, n, F, F4);
     return check_launch("agg_table");
 }
 
@@ -866,8 +937,7 @@ int launch_agg_bwd_pre(const float* out, const float* dout, long ldo, const floa
 int launch_agg_dx(const float* rowout, long ldro, const float* dxc, long ldc, const float* V, long n, int F, int F4,
                   int H, float* dX, long lddx, float* dq, cudaStream_t s) {
     if (n <= 0) return 0;
-    const long total = n * F;
-    agg_dx_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(rowout, ldro, dxc, ldc, V, n, F, F4, H, dX, lddx, dq);
+    agg_dx_kernel<<<(unsigned)((n + 8 * DX_R - 1) / (8 * DX_R)), 256, 0, s>>>(rowout, ldro, dxc, ldc, V, n, F, F4, H, dX, lddx, dq);
     return check_launch("agg_dx");
 }
 

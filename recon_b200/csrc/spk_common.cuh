@@ -55,10 +55,10 @@ __device__ __forceinline__ float selh(int h, const float (&v)[HT]) {
     return r;
 }
 
-// CTA-wide (8 warps) deterministic sum of the partial rows [t0, t1) of `part` (row stride ld, `len`
+// CTA-wide (NW warps, default 8) deterministic sum of the partial rows [t0, t1) of `part` (row stride ld, `len`
 // floats used). Warp w adds rows t0+w, t0+w+8, ... in ascending order with 4 rows of loads in flight,
 // then the 8 warp sums are added in warp order. Result in red[0 .. len). NREG >= ceil(len / 32).
-template <int NREG>
+template <int NREG, int NW = SPK_WARPS_PER_CTA>
 __device__ __forceinline__ void cta_sum_partials(const float* __restrict__ part, long ld, int t0, int t1, int len,
                                                  float* red, int red_ld) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -66,21 +66,21 @@ __device__ __forceinline__ void cta_sum_partials(const float* __restrict__ part,
 #pragma unroll
     for (int k = 0; k < NREG; ++k) acc[k] = 0.f;
     int t = t0 + wid;
-    for (; t + 3 * SPK_WARPS_PER_CTA < t1; t += 4 * SPK_WARPS_PER_CTA) {
+    for (; t + 3 * NW < t1; t += 4 * NW) {
         float v[4][NREG];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int k = 0; k < NREG; ++k) {
                 const int c = lane + 32 * k;
-                v[u][k] = c < len ? part[(long)(t + u * SPK_WARPS_PER_CTA) * ld + c] : 0.f;
+                v[u][k] = c < len ? part[(long)(t + u * NW) * ld + c] : 0.f;
             }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int k = 0; k < NREG; ++k) acc[k] += v[u][k];
     }
-    for (; t < t1; t += SPK_WARPS_PER_CTA) {
+    for (; t < t1; t += NW) {
 #pragma unroll
         for (int k = 0; k < NREG; ++k) {
             const int c = lane + 32 * k;
@@ -93,10 +93,10 @@ __device__ __forceinline__ void cta_sum_partials(const float* __restrict__ part,
         if (c < len) red[wid * red_ld + c] = acc[k];
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < len; c += SPK_CTA_THREADS) {
+    for (int c = threadIdx.x; c < len; c += (NW * 32)) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < SPK_WARPS_PER_CTA; ++w) s += red[w * red_ld + c];
+        for (int w = 0; w < NW; ++w) s += red[w * red_ld + c];
         red[c] = s;
     }
     __syncthreads();

@@ -365,7 +365,8 @@ static int launch_seg_t(const SegGatherArgs& a, cudaStream_t s) {
     const int var = seg_variant();
     if (a.n_seg > 0) {
         const unsigned grid = (a.n_seg + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        if (var == 1) seg_gather_kernel<NCH, U0, 4><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+        if (var == 1 && NCH == 1) seg_gather_kernel<NCH, U0, 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);   // narrow rows: 6 CTAs/SM measured best
+        else if (var == 1) seg_gather_kernel<NCH, U0, 4><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         else if (var == 4) seg_gather_kernel<NCH, U0, 5><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         else if (var == 5) seg_gather_kernel<NCH, U0, 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         else if (var == 6) seg_gather_kernel<NCH, (U0 > 2 ? U0 / 2 : U0), 6><<<grid, SPK_CTA_THREADS, 0, s>>>(a);

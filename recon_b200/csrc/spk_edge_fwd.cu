@@ -220,18 +220,20 @@ edge_fwd_tasks_kernel(const EdgeFwdArgs a) {
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.nanflag, 1);
 }
 
-// One CTA per hub row: the 8 warps add disjoint, interleaved subsets of the task partials (4 loads in
+// One CTA per hub row (32 warps so that a hub with thousands of task partials keeps enough loads in flight): the warps add disjoint, interleaved subsets of the task partials (4 loads in
 // flight each), then the 8 warp sums are added in warp order -> fixed summation tree, run-to-run identical.
+template <int NCH> struct FinCfg { static constexpr int NW = (NCH <= 2) ? 32 : 16; };   // warps of the finalize CTA
+
 template <int NCH, int HT>
-__global__ void __launch_bounds__(SPK_CTA_THREADS)
+__global__ void __launch_bounds__(FinCfg<NCH>::NW * 32)
 edge_fwd_hub_finalize_kernel(const EdgeFwdArgs a) {
-    __shared__ __align__(16) float red[SPK_WARPS_PER_CTA][NCH * 128 + 2 * SPK_MAX_HEADS];
+    __shared__ __align__(16) float red[FinCfg<NCH>::NW][NCH * 128 + 2 * SPK_MAX_HEADS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int hub = blockIdx.x;
     const int row = __ldg(a.hub.hub_seg + hub);
     const int t0 = __ldg(a.hub.hub_task_ptr + hub), t1 = __ldg(a.hub.hub_task_ptr + hub + 1);
     const int len = a.g.Wd4 * 4 + 2 * SPK_MAX_HEADS;         // floats used per partial row
-    cta_sum_partials<NCH * 4 + 1>(a.hub.partial, a.hub.ldpart, t0, t1, len, &red[0][0], NCH * 128 + 2 * SPK_MAX_HEADS);
+    cta_sum_partials<NCH * 4 + 1, FinCfg<NCH>::NW>(a.hub.partial, a.hub.ldpart, t0, t1, len, &red[0][0], NCH * 128 + 2 * SPK_MAX_HEADS);
     if (wid != 0) return;
     int hc[NCH];
     FwdAcc<NCH, HT> st;
@@ -521,7 +523,7 @@ static int launch_fwd_t(const EdgeFwdArgs& a, cudaStream_t s) {
             const unsigned grid = (a.hub.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS;
             edge_fwd_stream_kernel<NCH, HT, HAS2, true><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
             if (int rc = check_launch("edge_fwd_stream_tasks")) return rc;
-            edge_fwd_hub_finalize_kernel<NCH, HT><<<a.hub.n_hubs, SPK_CTA_THREADS, 0, s>>>(a);
+            edge_fwd_hub_finalize_kernel<NCH, HT><<<a.hub.n_hubs, FinCfg<NCH>::NW * 32, 0, s>>>(a);
             if (int rc = check_launch("edge_fwd_hub_finalize")) return rc;
         }
         return 0;
@@ -535,7 +537,7 @@ static int launch_fwd_t(const EdgeFwdArgs& a, cudaStream_t s) {
         const unsigned grid = (a.hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
         edge_fwd_tasks_kernel<NCH, HT, HAS2><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("edge_fwd_tasks")) return rc;
-        edge_fwd_hub_finalize_kernel<NCH, HT><<<a.hub.n_hubs, SPK_CTA_THREADS, 0, s>>>(a);
+        edge_fwd_hub_finalize_kernel<NCH, HT><<<a.hub.n_hubs, FinCfg<NCH>::NW * 32, 0, s>>>(a);
         if (int rc = check_launch("edge_fwd_hub_finalize")) return rc;
     }
     return 0;

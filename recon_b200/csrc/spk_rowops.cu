@@ -24,6 +24,40 @@ rownorm_kernel(const float* __restrict__ x, long ldx, float* __restrict__ y, lon
     for (int c = lane; c < width; c += 32) yr[c] = xr[c] * inv;
 }
 
+// even width, 8-byte aligned rows, width <= 64 * NV: a lane keeps its NV float2 of a row in registers (one pass over
+// memory); a warp handles R consecutive rows with all their loads issued up front (narrow rows need the extra loads in flight)
+template <int NV, int R>
+__global__ void __launch_bounds__(256)
+rownorm_vec2_kernel(const float* __restrict__ x, long ldx, float* __restrict__ y, long ldy, long n_rows, int w2) {
+    const int lane = threadIdx.x & 31;
+    const long row0 = ((long)blockIdx.x * 8 + (threadIdx.x >> 5)) * R;
+    float2 v[R][NV];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const float2* xr = reinterpret_cast<const float2*>(x + (row0 + r) * ldx);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            v[r][k] = (row0 + r < n_rows && c < w2) ? xr[c] : make_float2(0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (row0 + r >= n_rows) break;
+        float ss = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) ss = fmaf(v[r][k].x, v[r][k].x, fmaf(v[r][k].y, v[r][k].y, ss));
+        ss = warp_sum(ss);
+        const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+        float2* yr = reinterpret_cast<float2*>(y + (row0 + r) * ldy);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            if (c < w2) yr[c] = make_float2(v[r][k].x * inv, v[r][k].y * inv);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 residual_norm_kernel(const float* __restrict__ ew, long lde, const float* __restrict__ x2, long ldx,
                      const float* __restrict__ mask, float* __restrict__ out, long ldo,
@@ -77,7 +111,11 @@ __global__ void mask_from_index_kernel(const long long* __restrict__ idx, long n
 
 int rownorm(const float* x, long ldx, float* y, long ldy, long n_rows, int width, cudaStream_t s) {
     if (n_rows <= 0) return 0;
-    rownorm_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(x, ldx, y, ldy, n_rows, width);
+    const bool vec2 = (width % 2 == 0) && width <= 256 && (ldx % 2 == 0) && (ldy % 2 == 0) &&
+                      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 7) == 0;
+    if (vec2 && width <= 64) rownorm_vec2_kernel<1, 4><<<(unsigned)((n_rows + 31) / 32), 256, 0, s>>>(x, ldx, y, ldy, n_rows, width / 2);
+    else if (vec2) rownorm_vec2_kernel<4, 1><<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(x, ldx, y, ldy, n_rows, width / 2);
+    else rownorm_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(x, ldx, y, ldy, n_rows, width);
     return check_launch("rownorm");
 }
 int residual_norm(const float* ew, long lde, const float* x2, long ldx, const float* mask, float* out, long ldo,

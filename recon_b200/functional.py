@@ -231,7 +231,7 @@ def seg_gather(ptr, src, pos, hubs, G, ldg, rec, geom, dst, n_seg, tag):
     s.geom = geom.struct()
     part = _hub_partial(hubs, geom.Wd, G.device)
     hubs.fill(s.hub, part, geom.Wd)
-    _lib.current_tag = tag
+    _lib.current_tag = f"{tag}:w{geom.Wd}"
     try:
         _lib.check(_lib.load().spk_edge_attn_bwd_segments(C.byref(s), _lib.stream_ptr()), "edge_attn_bwd_segments")
     finally:

@@ -16,6 +16,7 @@ from . import _lib
 
 HUB_THRESH = 512      # segments longer than this are split ...
 HUB_CHUNK = 256       # ... into tasks of this many edges
+HUB_MAX_TASKS = 4096  # ... but never more tasks than this per segment (longer tasks instead; long tasks are a tail, keep it high)
 
 
 class HubSet:
@@ -34,15 +35,19 @@ class HubSet:
         self.n_hubs = int(hub_seg.numel())
         if self.n_hubs == 0:
             return
-        ntask = (deg[hub_seg] + chunk - 1) // chunk
+        # at most HUB_MAX_TASKS partials per hub (the finalize kernel adds them with one CTA): giant hubs get longer tasks
+        hdeg = deg[hub_seg]
+        hchunk = torch.clamp(((hdeg + HUB_MAX_TASKS - 1) // HUB_MAX_TASKS + 31) // 32 * 32, min=chunk)
+        ntask = (hdeg + hchunk - 1) // hchunk
         tptr = torch.zeros(self.n_hubs + 1, dtype=torch.int64, device=ptr.device)
         tptr[1:] = torch.cumsum(ntask, 0)
         self.n_tasks = int(tptr[-1].item())
         task_hub = torch.repeat_interleave(torch.arange(self.n_hubs, device=ptr.device), ntask)
         local = torch.arange(self.n_tasks, device=ptr.device) - tptr[task_hub]
         seg = hub_seg[task_hub]
-        beg = ptr64[seg] + local * chunk
-        end = torch.minimum(beg + chunk, ptr64[seg + 1])
+        tchunk = hchunk[task_hub]
+        beg = ptr64[seg] + local * tchunk
+        end = torch.minimum(beg + tchunk, ptr64[seg + 1])
         self.task_seg = seg.int().contiguous()
         self.task_beg = beg.int().contiguous()
         self.task_end = end.int().contiguous()
