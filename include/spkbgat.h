@@ -144,6 +144,46 @@ typedef struct {
 } spk_seg_gather_args;
 int spk_edge_attn_bwd_segments(const spk_seg_gather_args* args, spk_stream_t stream);
 
+/* ---- K3'/K4': column-major fused backward of a projected layer group. Same outputs as spk_edge_attn_bwd_rows followed by
+ *      spk_edge_attn_bwd_segments over the CSC (G, rec, dP1~, dP2~), but every edge is visited once, from its gathered
+ *      node: a node pass (dnum, per-row scalars), one pass over the columns (P2~[j] in registers, gathers dnum[i] and the
+ *      cache-resident P3~[k], writes the (w, ds) records and dP2~[j]) and a row-sum pass over the records. The relation
+ *      pass (dP3~) stays spk_edge_attn_bwd_segments. csc_t1 / csc_t2 are t1 / t2 gathered into CSC order. ---- */
+typedef struct {
+    const int32_t* rowptr;
+    const int32_t* colptr; const int32_t* csc_row; const int32_t* csc_pos; const int32_t* csc_t1; const int32_t* csc_t2;
+    const float* P1; int64_t ld1;
+    const float* P2; int64_t ld2;
+    const float* P3; int64_t ld3;
+    const float* mask; int64_t mask_stride;      /* [H][E] CSR-order dropout multipliers or null */
+    const float* out; const float* dout; int64_t ldo;
+    const float* den; const float* sw;           /* [n_rows, H] from spk_edge_attn_fwd */
+    float* G; int64_t ldg;                       /* [n_rows, ldg] dnum */
+    float* rowsc;                                /* [n_rows, H, 4] scratch */
+    float* dP1; int64_t ldd1;                    /* [n_rows, width] */
+    float* dP2; int64_t ldd2;                    /* [n_cols, width] */
+    float* rec;                                  /* [E, 2H] (w, ds) in CSR order */
+    int32_t n_rows; int32_t n_cols; int32_t apply_elu; float alpha;
+    spk_geom geom;
+    spk_hub_tasks row_hub;                       /* hub rows (no partial buffer needed) */
+    spk_hub_tasks col_hub;                       /* hub columns; partial [n_tasks, ldpart >= width] */
+} spk_edge_bwd_fused_args;
+int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* args, spk_stream_t stream);
+
+/* ---- K3"/K4": the same backward for graphs without 2-hop edges, with the per-edge dot t = dnum_i . m_e split between the
+ *      column pass (dnum_i . P2[j], P2~[j] in registers) and the relation pass (dnum_i . P3[k], P3~[k] in registers), the two
+ *      passes that gather dnum_i anyway: no projected row is gathered per edge at all. Computes G, dP1~, dP2~ AND dP3~.
+ *      rec4 [E, H, 4] and dsv [E, H] are scratch in CSR order. ---- */
+typedef struct {
+    spk_edge_bwd_fused_args base;                /* csc_t2 must be null; rec unused; col_hub as there */
+    const int32_t* relptr; const int32_t* rel_row; const int32_t* rel_pos;
+    float* rec4; float* dsv;
+    float* dP3; int64_t ldd3;                    /* [n_rel, width] */
+    int32_t n_rel; int32_t reserved;
+    spk_hub_tasks rel_hub;                       /* relation segments as tasks; partial [n_tasks, ldpart >= width] */
+} spk_edge_bwd_split_args;
+int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* args, spk_stream_t stream);
+
 /* ---- K2'/K3': "aggregate-then-project" variant for layer groups whose input is narrower than their projection
  *      (layer 1: in=50, nrela=50 against heads*out=200). Same reference lines as K2/K3 (GAT/layers.py:124-175 and
  *      their autograd); the sum over a row's edges is linear in [x_i | x_j | r_k], so the edges gather the INPUT

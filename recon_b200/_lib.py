@@ -61,6 +61,31 @@ class SegGatherArgs(C.Structure):
                 ("geom", Geom), ("hub", HubTasks)]
 
 
+class EdgeBwdFusedArgs(C.Structure):
+    _fields_ = [("rowptr", C.c_void_p),
+                ("colptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_pos", C.c_void_p), ("csc_t1", C.c_void_p),
+                ("csc_t2", C.c_void_p),
+                ("P1", C.c_void_p), ("ld1", C.c_int64), ("P2", C.c_void_p), ("ld2", C.c_int64),
+                ("P3", C.c_void_p), ("ld3", C.c_int64),
+                ("mask", C.c_void_p), ("mask_stride", C.c_int64),
+                ("out", C.c_void_p), ("dout", C.c_void_p), ("ldo", C.c_int64),
+                ("den", C.c_void_p), ("sw", C.c_void_p),
+                ("G", C.c_void_p), ("ldg", C.c_int64), ("rowsc", C.c_void_p),
+                ("dP1", C.c_void_p), ("ldd1", C.c_int64), ("dP2", C.c_void_p), ("ldd2", C.c_int64),
+                ("rec", C.c_void_p),
+                ("n_rows", C.c_int32), ("n_cols", C.c_int32), ("apply_elu", C.c_int32), ("alpha", C.c_float),
+                ("geom", Geom), ("row_hub", HubTasks), ("col_hub", HubTasks)]
+
+
+class EdgeBwdSplitArgs(C.Structure):
+    _fields_ = [("base", EdgeBwdFusedArgs),
+                ("relptr", C.c_void_p), ("rel_row", C.c_void_p), ("rel_pos", C.c_void_p),
+                ("rec4", C.c_void_p), ("dsv", C.c_void_p),
+                ("dP3", C.c_void_p), ("ldd3", C.c_int64),
+                ("n_rel", C.c_int32), ("reserved", C.c_int32),
+                ("rel_hub", HubTasks)]
+
+
 class AggGeom(C.Structure):
     _fields_ = [("n_heads", C.c_int32), ("f_chunks", C.c_int32), ("r_chunks", C.c_int32), ("lz", C.c_int32)]
 
@@ -122,6 +147,8 @@ SIGNATURES = {
     "spk_edge_attn_fwd": (_I32, [C.POINTER(EdgeFwdArgs), _VP]),
     "spk_edge_attn_bwd_rows": (_I32, [C.POINTER(EdgeBwdRowsArgs), _VP]),
     "spk_edge_attn_bwd_segments": (_I32, [C.POINTER(SegGatherArgs), _VP]),
+    "spk_edge_attn_bwd_fused": (_I32, [C.POINTER(EdgeBwdFusedArgs), _VP]),
+    "spk_edge_attn_bwd_split": (_I32, [C.POINTER(EdgeBwdSplitArgs), _VP]),
     "spk_spmm_rowsum_fwd": (_I32, [_VP, _VP, _VP, _I64, _I32, _VP, _I64, _I32, _VP]),
     "spk_spmm_rowsum_bwd": (_I32, [_VP, _VP, _I64, _I32, _VP, _I64, _I64, _VP]),
     "spk_rownorm": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _VP]),

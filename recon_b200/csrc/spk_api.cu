@@ -3,6 +3,7 @@
 #include "../../include/spkbgat.h"
 #include "spk_common.cuh"
 #include "spk_edge.cuh"
+#include "spk_edge_bwd_fused.cuh"
 #include "spk_agg.cuh"
 #include "spk_gemm.cuh"
 #include "spk_graph.cuh"
@@ -227,6 +228,66 @@ int spk_edge_attn_bwd_segments(const spk_seg_gather_args* p, spk_stream_t stream
         return 1;
     }
     return launch_seg_gather(a, (cudaStream_t)stream);
+}
+
+static int fused_args_of(const spk_edge_bwd_fused_args* p, BwdFusedArgs& a, const char* who);
+
+int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* p, spk_stream_t stream) {
+    BwdFusedArgs a;
+    if (int rc = fused_args_of(p, a, "edge_attn_bwd_fused")) return rc;
+    if (reinterpret_cast<uintptr_t>(p->rec) & 7) { set_error("edge_attn_bwd_fused: rec must be 8-byte aligned"); return 1; }
+    return launch_edge_bwd_fused(a, (cudaStream_t)stream);
+}
+
+int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* q, spk_stream_t stream) {
+    BwdSplitArgs a;
+    if (int rc = fused_args_of(&q->base, a.f, "edge_attn_bwd_split")) return rc;
+    if (q->base.csc_t2 != nullptr) { set_error("edge_attn_bwd_split: graphs with 2-hop edges are not supported"); return 1; }
+    if ((q->ldd3 & 3) || q->ldd3 < q->base.geom.width || !aligned16(q->dP3) || !aligned16(q->rec4) ||
+        (reinterpret_cast<uintptr_t>(q->dsv) & 3)) {
+        set_error("edge_attn_bwd_split: bad leading dimension or alignment");
+        return 1;
+    }
+    a.colptr = a.f.colptr; a.csc_row = a.f.csc_row; a.csc_pos = a.f.csc_pos; a.csc_t1 = a.f.csc_t1;
+    a.relptr = q->relptr; a.rel_row = q->rel_row; a.rel_pos = q->rel_pos;
+    a.P2 = a.f.P2; a.ld2 = a.f.ld2; a.P3 = a.f.P3; a.ld3 = a.f.ld3; a.mask = a.f.mask; a.mask_stride = a.f.mask_stride;
+    a.G = a.f.G; a.ldg = a.f.ldg; a.rowsc = a.f.rowsc; a.rec4 = q->rec4; a.dsv = q->dsv;
+    a.dP2 = a.f.dP2; a.ldd2 = a.f.ldd2; a.dP3 = q->dP3; a.ldd3 = q->ldd3;
+    a.n_cols = a.f.n_cols; a.n_rel = q->n_rel; a.g = a.f.g; a.alpha = a.f.alpha;
+    a.col_hub = a.f.col_hub;
+    a.rel_hub = hub_of(q->rel_hub);
+    if (a.rel_hub.n_tasks > 0 && (a.rel_hub.ldpart < q->base.geom.width || (a.rel_hub.ldpart & 3) || !aligned16(a.rel_hub.partial))) {
+        set_error("edge_attn_bwd_split: relation hub partial buffer needs ldpart >= width");
+        return 1;
+    }
+    return launch_edge_bwd_split(a, (cudaStream_t)stream);
+}
+
+static int fused_args_of(const spk_edge_bwd_fused_args* p, BwdFusedArgs& a, const char* who) {
+    if (!geom_ok(p->geom, &a.g, who)) return 1;
+    if ((p->ld1 & 3) || (p->ld2 & 3) || (p->ld3 & 3) || (p->ldg & 3) || (p->ldd1 & 3) || (p->ldd2 & 3) ||
+        p->ldg < p->geom.n_heads * p->geom.d_pad || p->ldd1 < p->geom.width || p->ldd2 < p->geom.width ||
+        p->ld1 < p->geom.width || p->ld2 < p->geom.width || p->ld3 < p->geom.width ||
+        !aligned16(p->P1) || !aligned16(p->P2) || !aligned16(p->P3) || !aligned16(p->G) || !aligned16(p->dP1) ||
+        !aligned16(p->dP2) || !aligned16(p->rowsc)) {
+        set_error("%s: bad leading dimension or alignment", who);
+        return 1;
+    }
+    a.rowptr = p->rowptr; a.colptr = p->colptr; a.csc_row = p->csc_row; a.csc_pos = p->csc_pos;
+    a.csc_t1 = p->csc_t1; a.csc_t2 = p->csc_t2;
+    a.P1 = p->P1; a.ld1 = p->ld1; a.P2 = p->P2; a.ld2 = p->ld2; a.P3 = p->P3; a.ld3 = p->ld3;
+    a.mask = p->mask; a.mask_stride = p->mask_stride;
+    a.out = p->out; a.dout = p->dout; a.ldo = p->ldo; a.den = p->den; a.sw = p->sw;
+    a.G = p->G; a.ldg = p->ldg; a.rowsc = p->rowsc; a.dP1 = p->dP1; a.ldd1 = p->ldd1; a.dP2 = p->dP2; a.ldd2 = p->ldd2;
+    a.rec = p->rec; a.n_rows = p->n_rows; a.n_cols = p->n_cols; a.alpha = p->alpha; a.apply_elu = p->apply_elu;
+    a.out_vec = (p->geom.d_head % 4 == 0) && (p->ldo % 4 == 0) && aligned16(p->out) && aligned16(p->dout);
+    a.row_hub = hub_of(p->row_hub);
+    a.col_hub = hub_of(p->col_hub);
+    if (a.col_hub.n_tasks > 0 && (a.col_hub.ldpart < p->geom.width || (a.col_hub.ldpart & 3) || !aligned16(a.col_hub.partial))) {
+        set_error("%s: hub partial buffer needs ldpart >= width", who);
+        return 1;
+    }
+    return 0;
 }
 
 static bool agg_geom_ok(const spk_agg_geom& g, AggGeom* out, const char* who) {

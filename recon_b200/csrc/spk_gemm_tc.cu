@@ -15,6 +15,7 @@
 // The projection GEMMs this serves are the re-associated `a.mm(edge_h)` of GAT/layers.py:137
 //  and its autograd products; weights are tiny so B is split once per call on the device.
 #include <cuda.h>
+#include <stdlib.h>
 #include "spk_common.cuh"
 #include "spk_gemm.cuh"
 
@@ -78,6 +79,7 @@ struct TcParams {
     float* C; long ldc; long M; int N; int K; int BN; int n_tiles_n; int stages; int accumulate; int c_vec;
     int act;                                    // epilogue: 0 = none, 1 = ELU (GAT/layers.py:175) on the final value
     int c_tma;                                  // epilogue stores through shared memory + TMA (coalesced 128 B rows)
+    int raw_hi;                                 // the MMA reads the raw fp32 tile as "hi" (kind::tf32 ignores the low 13 mantissa bits)
 };
 
 // ELU(x) = x (x > 0) else expm1(x); same evaluation as the edge kernels (degree-5 polynomial near 0)
@@ -196,7 +198,8 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
                     h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
                     h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi0 + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                    if (!p.raw_hi)
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi0 + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA's async proxy
@@ -362,6 +365,13 @@ int make_map(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld, i
 
 int gemm_tc_ldt(int K) { return (K + 3) / 4 * 4; }
 
+// SPK_TC_RAW_HI=0 restores the explicit hi rewrite in the splitter (default: the raw tile is the hi operand)
+static int tc_raw_hi() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_TC_RAW_HI"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 int gemm_nn_tc_supported(const float* A, long lda, long M, int N, int K) {
     return M >= 1 && N >= 1 && K >= 1 && (lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && lda >= K;
 }
@@ -402,7 +412,7 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     TcParams p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.n_tiles_n = n_tiles_n; p.stages = stages;
     p.accumulate = accumulate; p.act = act;
-    p.c_vec = c_vec; p.c_tma = c_tma;
+    p.c_vec = c_vec; p.c_tma = c_tma; p.raw_hi = tc_raw_hi();
     static int smem_set = 0;
     if (smem_set < smem) {
         if (cudaFuncSetAttribute(gemm_nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
@@ -448,26 +458,35 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
 
 struct TnParams {
     float* part; long M; int Ka; int Nb; int BN; int n_tiles_n; int n_tiles_k; int splits; long m_per_split; int stages;
+    int raw_hi;
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// Decoupled rings: the raw tiles (TMA destination; read by the MMA as the "hi" operands) live in a ring of
+// p.stages slots so the DRAM latency of both streamed operands is covered, the split-off "lo" tiles in a
+// 2-slot ring written by the splitter warps right before the MMA consumes them.
+constexpr int TN_LO_SLOTS = 2;
+constexpr int TN_SPLIT_WARPS = 8;
+constexpr int TN_THREADS = (2 + TN_SPLIT_WARPS + 4) * 32;      // TMA, MMA, splitters, epilogue
+
+__global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const TnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 2 * TN_LO_SLOTS + 1];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int nbc = p.BN / 32;                                     // B chunks
-    const uint32_t half = (uint32_t)(TN_ACH + nbc) * TN_CHUNK;     // raw/hi part of a stage; lo part follows
-    const uint32_t stage_bytes = 2u * half;
-    auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
-    auto b_hi = [&](int s) { return base + (uint32_t)s * stage_bytes + TN_ACH * TN_CHUNK; };
+    const uint32_t half = (uint32_t)(TN_ACH + nbc) * TN_CHUNK;     // one slot: A chunks, then B chunks
+    const uint32_t b_off = TN_ACH * TN_CHUNK;
+    auto raw = [&](int s) { return base + (uint32_t)s * half; };
+    auto lo = [&](int l) { return base + (uint32_t)(p.stages + l) * half; };
     const uint32_t bar0 = smem_u32(bars);
-    auto full = [&](int s) { return bar0 + 8u * s; };
-    auto conv = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
-    auto empty = [&](int s) { return bar0 + 8u * (2 * TC_MAX_STAGES + s); };
-    const uint32_t tfull = bar0 + 8u * (3 * TC_MAX_STAGES);
+    auto full = [&](int s) { return bar0 + 8u * s; };                                       // TMA -> splitter, MMA
+    auto rawfree = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };                  // MMA commit -> TMA
+    auto conv = [&](int l) { return bar0 + 8u * (2 * TC_MAX_STAGES + l); };                 // splitter -> MMA
+    auto lofree = [&](int l) { return bar0 + 8u * (2 * TC_MAX_STAGES + TN_LO_SLOTS + l); }; // MMA commit -> splitter
+    const uint32_t tfull = bar0 + 8u * (2 * TC_MAX_STAGES + 2 * TN_LO_SLOTS);
 
     const int tile = blockIdx.x % (p.n_tiles_k * p.n_tiles_n);
     const int split = blockIdx.x / (p.n_tiles_k * p.n_tiles_n);
@@ -480,7 +499,8 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
-        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(rawfree(s), 1); }
+        for (int l = 0; l < TN_LO_SLOTS; ++l) { mbar_init(conv(l), TN_SPLIT_WARPS * 32); mbar_init(lofree(l), 1); }
         mbar_init(tfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -498,12 +518,12 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t ph = (kb / p.stages) & 1u;
-                mbar_wait(empty(s), ph ^ 1u);
+                mbar_wait(rawfree(s), ph ^ 1u);
                 mbar_arrive_expect_tx(full(s), half);
-                // rows beyond `mend` belong to the next split: clamp by loading them and zeroing in the splitter
+                // rows beyond `mend` belong to the next split: they are loaded and zeroed by the splitter
                 const int m0 = (int)(mbeg + (long)kb * TN_BKM);
-                for (int c = 0; c < TN_ACH; ++c) tma_load_2d(a_hi(s) + c * TN_CHUNK, &tmX, full(s), ka0 + 32 * c, m0);
-                for (int c = 0; c < nbc; ++c) tma_load_2d(b_hi(s) + c * TN_CHUNK, &tmG, full(s), nb0 + 32 * c, m0);
+                for (int c = 0; c < TN_ACH; ++c) tma_load_2d(raw(s) + c * TN_CHUNK, &tmX, full(s), ka0 + 32 * c, m0);
+                for (int c = 0; c < nbc; ++c) tma_load_2d(raw(s) + b_off + c * TN_CHUNK, &tmG, full(s), nb0 + 32 * c, m0);
             }
         }
     } else if (warp == 1) {
@@ -511,13 +531,12 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (kb / p.stages) & 1u;
-                mbar_wait(full(s), ph);
-                mbar_wait(conv(s), ph);
+                const int s = kb % p.stages, l = kb % TN_LO_SLOTS;
+                mbar_wait(full(s), (kb / p.stages) & 1u);
+                mbar_wait(conv(l), (kb / TN_LO_SLOTS) & 1u);
                 tc_fence_after();
-                const uint64_t dah = make_mnmajor_sw128_desc(a_hi(s)), dal = make_mnmajor_sw128_desc(a_hi(s) + half);
-                const uint64_t dbh = make_mnmajor_sw128_desc(b_hi(s)), dbl = make_mnmajor_sw128_desc(b_hi(s) + half);
+                const uint64_t dah = make_mnmajor_sw128_desc(raw(s)), dal = make_mnmajor_sw128_desc(lo(l));
+                const uint64_t dbh = make_mnmajor_sw128_desc(raw(s) + b_off), dbl = make_mnmajor_sw128_desc(lo(l) + b_off);
 #pragma unroll
                 for (int ks = 0; ks < TN_BKM / 8; ++ks) {
                     const uint64_t o = (uint64_t)(ks * (1024 >> 4));     // next 8-row group
@@ -525,36 +544,39 @@ gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     tc_mma_tf32(tmem_base, dah + o, dbl + o, idesc, 1u);
                     tc_mma_tf32(tmem_base, dah + o, dbh + o, idesc, 1u);
                 }
-                tc_commit(empty(s));
+                tc_commit(rawfree(s));
+                tc_commit(lofree(l));
             }
             tc_commit(tfull);
         }
-    } else if (warp < 6) {                                         // ---- splitter: both tiles, raw -> (hi, lo)
+    } else if (warp < 2 + TN_SPLIT_WARPS) {                        // ---- splitter: both tiles, raw -> (hi in place, lo)
         const int t = threadIdx.x - 64;
         const int n16 = (int)(half / 16);
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % p.stages;
-            const uint32_t ph = (kb / p.stages) & 1u;
-            mbar_wait(full(s), ph);
-            const uint32_t hi0 = a_hi(s), lo0 = a_hi(s) + half;
+            const int s = kb % p.stages, l = kb % TN_LO_SLOTS;
+            mbar_wait(full(s), (kb / p.stages) & 1u);
+            mbar_wait(lofree(l), ((kb / TN_LO_SLOTS) & 1u) ^ 1u);
+            const uint32_t hi0 = raw(s), lo0 = lo(l);
             const long m0 = mbeg + (long)kb * TN_BKM;
             const int valid_rows = (int)(mend - m0 < TN_BKM ? mend - m0 : TN_BKM);   // rows past the split end count as 0
-            for (int i = t; i < n16; i += 128) {
+            for (int i = t; i < n16; i += TN_SPLIT_WARPS * 32) {
                 const uint32_t off = (uint32_t)i * 16u;
                 const int r = (i >> 3) & (TN_BKM - 1);             // row inside the 4 KB chunk (128 B per row)
                 float4 x;
                 asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi0 + off));
                 if (r >= valid_rows) x = make_float4(0.f, 0.f, 0.f, 0.f);
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l.x = x.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l.y = x.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l.z = x.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l.w = x.w - h.w;
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi0 + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                float4 h, l4;
+                h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); l4.x = x.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); l4.y = x.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); l4.z = x.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); l4.w = x.w - h.w;
+                // rows past the split end must read as zero, so they are rewritten even in raw-hi mode
+                if (!p.raw_hi || r >= valid_rows)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(hi0 + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l4.x), "f"(l4.y), "f"(l4.z), "f"(l4.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(conv(s));
+            mbar_arrive(conv(l));
         }
     } else {                                                       // ---- epilogue: TMEM -> partial[split][ka][nb]
         const int q = warp & 3;
@@ -629,10 +651,11 @@ TnPlan tn_plan(long M, int Ka, int Nb) {
     pl.splits = (int)((M + mps - 1) / mps);
     if (pl.splits < 1) pl.splits = 1;
     pl.m_per_split = mps;
-    const int stage_bytes = 2 * (TN_ACH + pl.BN / 32) * TN_CHUNK;
-    pl.stages = (225 * 1024 - 1024) / stage_bytes;
+    const int half = (TN_ACH + pl.BN / 32) * TN_CHUNK;              // one slot (A chunks + B chunks)
+    pl.stages = (225 * 1024 - 1024) / half - TN_LO_SLOTS;           // raw slots next to the 2 lo slots
     if (pl.stages > TC_MAX_STAGES) pl.stages = TC_MAX_STAGES;
-    pl.smem = pl.stages * stage_bytes + 1024;
+    if (pl.stages < 1) pl.stages = 1;
+    pl.smem = (pl.stages + TN_LO_SLOTS) * half + 1024;
     return pl;
 }
 }  // namespace
@@ -655,7 +678,7 @@ int gemm_tn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     if (int rc = make_map_tn(&tmG, B, M, Nb, ldb)) return rc;
     TnParams p;
     p.part = workspace; p.M = M; p.Ka = Ka; p.Nb = Nb; p.BN = pl.BN; p.n_tiles_n = pl.n_tiles_n; p.n_tiles_k = pl.n_tiles_k;
-    p.splits = pl.splits; p.m_per_split = pl.m_per_split; p.stages = pl.stages;
+    p.splits = pl.splits; p.m_per_split = pl.m_per_split; p.stages = pl.stages; p.raw_hi = tc_raw_hi();
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
@@ -666,7 +689,7 @@ int gemm_tn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
         attr_set = true;
     }
     const unsigned grid = (unsigned)(pl.n_tiles_k * pl.n_tiles_n * pl.splits);
-    gemm_tn_tc_kernel<<<grid, TC_THREADS, pl.smem, s>>>(tmX, tmG, p);
+    gemm_tn_tc_kernel<<<grid, TN_THREADS, pl.smem, s>>>(tmX, tmG, p);
     if (int rc = check_launch("gemm_tn_tc")) return rc;
     const long elems = (long)Ka * Nb;
     tn_reduce_tc_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, s>>>(workspace, pl.splits, elems, Nb, C, ldc, accumulate);

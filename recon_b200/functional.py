@@ -11,6 +11,7 @@ built from the reference-shaped parameters `a`, `a_2` with differentiable torch 
 tensors, so autograd chains dWn, dWr back to a and a_2.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -191,14 +192,72 @@ def edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanfl
     return out, den, sw
 
 
-def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, dP1, dP2, dP3):
-    """K3 + K4 launches. Fills dP1 [n_rows, Wd], dP2 [n_cols, Wd] (indexed by gathered node) and dP3 [R, Wd]."""
+# Backward schedule of the projected layer groups:
+#   "split": node pass + column pass + relation pass with the per-edge dot split between them (K3"/K4", no 2-hop edges)
+#   "fused": node pass + one column pass that also gathers P3~[k] (K3'/K4'), relation pass = K4
+#   "rows" : K3 over the rows, then K4 over columns and relations
+# "split" falls back to "rows" for graphs with 2-hop edges.
+BWD_MODE = os.environ.get("SPK_BWD_MODE", "split")
+
+
+def _fill_fused_args(f, graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, sw, G, ldg, rowsc, dP1, dP2, rec):
+    f.rowptr = graph.rowptr.data_ptr()
+    f.colptr = graph.colptr.data_ptr(); f.csc_row = graph.csc_row.data_ptr(); f.csc_pos = graph.csc_pos.data_ptr()
+    f.csc_t1 = graph.csc_t1.data_ptr(); f.csc_t2 = graph.csc_t2.data_ptr() if graph.csc_t2 is not None else None
+    f.P1 = P1.data_ptr(); f.ld1 = P1.stride(0); f.P2 = P2.data_ptr(); f.ld2 = P2.stride(0)
+    f.P3 = P3.data_ptr(); f.ld3 = P3.stride(0)
+    if mask_csr is not None:
+        f.mask = mask_csr.data_ptr(); f.mask_stride = mask_csr.stride(0)
+    f.out = out.data_ptr(); f.dout = dout.data_ptr(); f.ldo = out.stride(0)
+    assert dout.stride(0) == out.stride(0)
+    f.den = den.data_ptr(); f.sw = sw.data_ptr()
+    f.G = G.data_ptr(); f.ldg = ldg; f.rowsc = rowsc.data_ptr()
+    f.dP1 = dP1.data_ptr(); f.ldd1 = dP1.stride(0); f.dP2 = dP2.data_ptr(); f.ldd2 = dP2.stride(0)
+    f.rec = rec.data_ptr() if rec is not None else None
+    f.n_rows = graph.n_nodes; f.n_cols = graph.n_cols; f.apply_elu = int(apply_elu); f.alpha = float(alpha)
+    f.geom = geom.struct()
+    graph.row_hubs.fill(f.row_hub, None, 0)
+    part = _hub_partial(graph.col_hubs, geom.Wd, P1.device)
+    graph.col_hubs.fill(f.col_hub, part, geom.Wd)
+    return part
+
+
+def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, sw, dP1, dP2, dP3):
+    """Backward edge passes. Fills dP1 [n_rows, Wd], dP2 [n_cols, Wd] (indexed by gathered node) and dP3 [R, Wd]."""
     lib = _lib.load()
     graph.build_backward()
     n, dev = graph.n_nodes, P1.device
     ldg = (geom.Dt + 7) // 8 * 8
     G = torch.empty(n, ldg, dtype=torch.float32, device=dev)
-    rec = torch.empty(max(1, graph.n_edges), 2 * geom.H, dtype=torch.float32, device=dev)
+    mode = BWD_MODE if sw is not None else "rows"
+    if mode == "split" and graph.t2 is not None:
+        mode = "rows"
+    ne = max(1, graph.n_edges)
+    if mode == "split":
+        q = _lib.EdgeBwdSplitArgs()
+        rowsc = torch.empty(max(1, n), geom.H, 4, dtype=torch.float32, device=dev)
+        rec4 = torch.empty(ne, geom.H, 4, dtype=torch.float32, device=dev)
+        dsv = torch.empty(ne, geom.H, dtype=torch.float32, device=dev)
+        keep = _fill_fused_args(q.base, graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, sw, G, ldg,
+                                rowsc, dP1, dP2, None)
+        q.relptr = graph.relptr.data_ptr(); q.rel_row = graph.rel_row.data_ptr(); q.rel_pos = graph.rel_pos.data_ptr()
+        q.rec4 = rec4.data_ptr(); q.dsv = dsv.data_ptr()
+        q.dP3 = dP3.data_ptr(); q.ldd3 = dP3.stride(0); q.n_rel = graph.n_rel
+        part3 = _hub_partial(graph.rel_hubs, geom.Wd, dev)
+        graph.rel_hubs.fill(q.rel_hub, part3, geom.Wd)
+        _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+        del keep, part3
+        return
+    rec = torch.empty(ne, 2 * geom.H, dtype=torch.float32, device=dev)
+    if mode == "fused":
+        f = _lib.EdgeBwdFusedArgs()
+        rowsc = torch.empty(max(1, n), geom.H, 4, dtype=torch.float32, device=dev)
+        keep = _fill_fused_args(f, graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, sw, G, ldg, rowsc,
+                                dP1, dP2, rec)
+        _lib.check(lib.spk_edge_attn_bwd_fused(C.byref(f), _lib.stream_ptr()), "edge_attn_bwd_fused")
+        del keep
+        seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, G, ldg, rec, geom, dP3, graph.n_rel, "rels")
+        return
     a = _lib.EdgeBwdRowsArgs()
     a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
     a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
@@ -270,7 +329,7 @@ class AttentionGroupFn(torch.autograd.Function):
             P1 = P[:, :Wd]
             P2 = dist.all_gather_rows(P[:, Wd:])
         out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
-        ctx.save_for_backward(X, Wn, Rel, Wr, P1, P2, P3, out, den, X_all if X_all is not None else X.new_empty(0))
+        ctx.save_for_backward(X, Wn, Rel, Wr, P1, P2, P3, out, den, sw, X_all if X_all is not None else X.new_empty(0))
         ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, ctx.mode = graph, geom, alpha, apply_elu, mask_csr, mode
         ctx.mark_non_differentiable(den, sw)
         return out, den, sw
@@ -279,7 +338,7 @@ class AttentionGroupFn(torch.autograd.Function):
     def backward(ctx, dout, _dden, _dsw):
         geom, graph, mode = ctx.geom, ctx.graph, ctx.mode
         dist = getattr(graph, "dist", None)
-        X, Wn, Rel, Wr, P1, P2, P3, out, den, X_all = ctx.saved_tensors
+        X, Wn, Rel, Wr, P1, P2, P3, out, den, sw, X_all = ctx.saved_tensors
         Wd = geom.Wd
         dout = dout.contiguous()
         n = X.shape[0]
@@ -289,7 +348,7 @@ class AttentionGroupFn(torch.autograd.Function):
         dX = dWn = None
         if mode == "local":
             dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=X.device)
-            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den,
+            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
                                dP[:, :Wd], dP[:, Wd:], dP3)
             if need_x:
                 dX = gemm_nn(dP, WnT)
@@ -298,7 +357,7 @@ class AttentionGroupFn(torch.autograd.Function):
         elif mode == "proj":
             dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=X.device)
             dP2_all = torch.empty_like(P2)      # partial over this rank's edges, all gathered nodes
-            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den,
+            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
                                dP[:, :Wd], dP2_all, dP3)
             dist.reduce_scatter_rows(dP2_all, dP[:, Wd:])
             del dP2_all
@@ -310,7 +369,7 @@ class AttentionGroupFn(torch.autograd.Function):
         else:                                   # "input"
             dP1 = torch.empty(n, Wd, dtype=torch.float32, device=X.device)
             dP2_all = torch.empty_like(P2)
-            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den,
+            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
                                dP1, dP2_all, dP3)
             dist.all_reduce(dP3)
             if need_x:
@@ -485,7 +544,7 @@ class AggGroupFn(torch.autograd.Function):
         _lib.check(lib.spk_agg_dx(_lib.ptr(rowout), rowout.stride(0), _lib.ptr(dXc), dXc.stride(0), _lib.ptr(V), n,
                                   geom.F, geom.Fx4, H, _lib.ptr(dX), dX.stride(0), _lib.ptr(dq), _lib.stream_ptr()),
                    "agg_dx")
-        dV = gemm_tn(X, dq) if ctx.needs_input_grad[3] else None
+        dV = gemm_tn(Xt[:, :geom.F], dq) if ctx.needs_input_grad[3] else None      # Xt rows start with x (16 B aligned stride)
         dq3 = dRc[:, H * Rp:H * Rp + H].contiguous()                      # [R, H]
         dRel = None
         if ctx.needs_input_grad[1]:

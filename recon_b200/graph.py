@@ -63,7 +63,7 @@ class HubSet:
             hub.task_seg = self.task_seg.data_ptr(); hub.task_beg = self.task_beg.data_ptr()
             hub.task_end = self.task_end.data_ptr(); hub.hub_seg = self.hub_seg.data_ptr()
             hub.hub_task_ptr = self.hub_task_ptr.data_ptr()
-            hub.partial = partial.data_ptr(); hub.ldpart = ldpart
+            hub.partial = partial.data_ptr() if partial is not None else None; hub.ldpart = ldpart
 
 
 def _key_bits(n):
@@ -151,7 +151,7 @@ class KGraph:
         self.t1 = _gather(t1, perm)
         self.t2 = _gather(t2, perm) if has2 else None
         self.row_hubs = HubSet(self.rowptr)
-        self.colptr = self.csc_row = self.csc_pos = self.col_hubs = None
+        self.colptr = self.csc_row = self.csc_pos = self.col_hubs = self.csc_t1 = self.csc_t2 = None
         self.relptr = self.rel_row = self.rel_pos = self.rel_hubs = None
         if build_backward:
             self.build_backward()
@@ -166,6 +166,8 @@ class KGraph:
         self.csc_pos = cpos
         self.csc_row = _gather(self.row, cpos)
         self.col_hubs = HubSet(self.colptr)
+        self.csc_t1 = _gather(self.t1, cpos)                     # relation ids in CSC order (column-major fused backward)
+        self.csc_t2 = _gather(self.t2, cpos) if self.t2 is not None else None
         m = 2 * e if self.t2 is not None else e
         rkeys = torch.empty(m, dtype=torch.int32, device=device)
         rvals = torch.empty(m, dtype=torch.int32, device=device)

@@ -197,6 +197,17 @@ def agg_path(request):
     SF.AGG_MODE = old
 
 
+@pytest.fixture(params=["split", "fused", "rows"])
+def bwd_path(request):
+    """Backward schedule of the projected layer groups (functional.BWD_MODE): split-dot column + relation passes
+    (default; graphs with 2-hop edges fall back to "rows"), column-major fused pass, or K3 rows + K4 columns."""
+    from recon_b200 import functional as SF
+    old = SF.BWD_MODE
+    SF.BWD_MODE = request.param
+    yield request.param
+    SF.BWD_MODE = old
+
+
 @pytest.mark.parametrize("name", ["layer_concat", "layer_noconcat_nhop"])
 def test_attention_layer_golden(name, agg_path):
     from recon_b200 import SpGraphAttentionLayer
@@ -269,7 +280,7 @@ def test_state_dict_keys_match_reference():
 
 # ---- seeded synthetic inputs against the oracle (C1 shape, uniform and Zipf with hub rows) ------------
 @pytest.mark.parametrize("alpha,n_nhop,p_drop", [(None, 0, 0.0), (1.1, 0, 0.0), (1.1, 20000, 0.3)])
-def test_model_vs_oracle_c1(alpha, n_nhop, p_drop, agg_path):
+def test_model_vs_oracle_c1(alpha, n_nhop, p_drop, agg_path, bwd_path):
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
     from oracle import ref_torch as O
@@ -304,7 +315,7 @@ def test_model_vs_oracle_c1(alpha, n_nhop, p_drop, agg_path):
         assert model.prepare_graph((edge, etype), nhop).row_hubs.n_hubs > 0      # the hub path was exercised
 
 
-def test_run_to_run_bit_identical(agg_path):
+def test_run_to_run_bit_identical(agg_path, bwd_path):
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
     from oracle import ref_torch as O
