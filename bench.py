@@ -127,7 +127,13 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = args.workload or ("c2" if args.gpus == 1 else "c4")
+    # default: the C2 shape per GPU (weak scaling): N GPUs run a graph with N x 2M entities / N x 20M edges, row-partitioned
+    # with the NCCL exchanges of SURVEY.md 8e. `--workload c4` runs the fixed 400M-edge shape (needs >= 4 GPUs of 180 GB).
+    workload = args.workload or ("c2" if world == 1 else f"c2x{world}")
+    if workload.startswith("c2x"):
+        k = int(workload[3:])
+        n0, e0, _, r0, a0, h0 = WORKLOADS["c2"]
+        WORKLOADS[workload] = (n0 * k, e0 * k, 0, r0, a0, h0)
 
     if args.impl == "reference":
         if rank != 0:
@@ -226,7 +232,7 @@ def main():
     balg = b_alg_bytes(n_, e1_, e2_)
     line = {"metric": "SpKBGAT fwd+bwd edges/sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if (world == 1 or workload.startswith("c2x")) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{workload}: N={n_} E1={e1_} E2={e2_} R={WORKLOADS[workload][3]} in={F_IN} "
                                    f"entity_out=[{D_OUT},{2 * D_OUT}] heads=[{HEADS},{HEADS}] rows: "
                                    f"{int(100 * WORKLOADS[workload][5])}% Pareto(alpha={WORKLOADS[workload][4]}) hubs + uniform",

@@ -175,7 +175,7 @@ int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* args, spk_stream_t st
  *      passes that gather dnum_i anyway: no projected row is gathered per edge at all. Computes G, dP1~, dP2~ AND dP3~.
  *      rec4 [E, H, 4] and dsv [E, H] are scratch in CSR order. ---- */
 typedef struct {
-    spk_edge_bwd_fused_args base;                /* csc_t2 must be null; rec unused; col_hub as there */
+    spk_edge_bwd_fused_args base;                /* csc_t2 must be null; rec unused; col_hub as there; row_hub.partial [n_tasks, >= 4] */
     const int32_t* relptr; const int32_t* rel_row; const int32_t* rel_pos;
     float* rec4; float* dsv;
     float* dP3; int64_t ldd3;                    /* [n_rel, width] */

@@ -767,13 +767,6 @@ int launch_agg_bwd_t(const AggBwdArgs& a, cudaStream_t s) {
 // ---- row-wise helpers ------------------------------------------------------------------------------
 // dhn = dOut * ELU'(hn) from the saved output (hn > 0: out = hn; else out = e^hn - 1, ELU' = out + 1, hn = log1p(out));
 // dden_h = -(dhn_h . hn_h) / den_h
-// log1p(x) on (-1, 0] as log(u) * x / (u - 1), u = fl(1 + x): the rounding of u cancels to first order (|rel err| ~ 2e-7)
-__device__ __forceinline__ float fast_log1p(float x) {
-    const float u = 1.0f + x;
-    const float d = u - 1.0f;
-    return d == 0.f ? x : __logf(u) * __fdividef(x, d);
-}
-
 __device__ __forceinline__ void bwd_pre_elem(float ov, float gv, int apply_elu, float& dh, float& p) {
     float hv = ov;
     dh = gv;

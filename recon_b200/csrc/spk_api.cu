@@ -255,6 +255,10 @@ int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* q, spk_stream_t strea
     a.dP2 = a.f.dP2; a.ldd2 = a.f.ldd2; a.dP3 = q->dP3; a.ldd3 = q->ldd3;
     a.n_cols = a.f.n_cols; a.n_rel = q->n_rel; a.g = a.f.g; a.alpha = a.f.alpha;
     a.col_hub = a.f.col_hub;
+    if (a.f.row_hub.n_tasks > 0 && (a.f.row_hub.partial == nullptr || a.f.row_hub.ldpart < 4)) {
+        set_error("edge_attn_bwd_split: row hub partial buffer [n_tasks, >= 4] required");
+        return 1;
+    }
     a.rel_hub = hub_of(q->rel_hub);
     if (a.rel_hub.n_tasks > 0 && (a.rel_hub.ldpart < q->base.geom.width || (a.rel_hub.ldpart & 3) || !aligned16(a.rel_hub.partial))) {
         set_error("edge_attn_bwd_split: relation hub partial buffer needs ldpart >= width");

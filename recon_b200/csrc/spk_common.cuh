@@ -20,6 +20,13 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// log1p(x) on (-1, 0] as log(u) * x / (u - 1), u = fl(1 + x): the rounding of u cancels to first order (|rel err| ~ 2e-7)
+__device__ __forceinline__ float fast_log1p(float x) {
+    const float u = 1.0f + x;
+    const float d = u - 1.0f;
+    return d == 0.f ? x : __logf(u) * __fdividef(x, d);
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
 }

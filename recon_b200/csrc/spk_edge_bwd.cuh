@@ -57,7 +57,7 @@ __device__ __forceinline__ void bwd_row_prologue(const EdgeBwdRowsArgs& a, int r
                 // out = ELU(h): h>0 -> out=h, d=1 ; else out=e^h-1, d=out+1, h=log1p(out)
                 const bool pos = o[k] > 0.f;
                 dh[k] = pos ? gg[k] : gg[k] * (o[k] + 1.f);
-                hv[k] = pos ? o[k] : (o[k] > -1.f ? log1pf(o[k]) : 0.f);
+                hv[k] = pos ? o[k] : (o[k] > -1.f ? fast_log1p(o[k]) : 0.f);
             } else {
                 dh[k] = gg[k];
                 hv[k] = o[k];

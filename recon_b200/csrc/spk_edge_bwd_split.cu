@@ -307,27 +307,46 @@ split_sum_kernel(const int* __restrict__ segptr, const int* __restrict__ idx, co
     if (lane < H) dst[(long)seg * ldd + qoff + lane] = selh<HT>(lane, u);
 }
 
-// one CTA per hub segment: thread-strided sums in ascending order, then a fixed tree over the CTA
+// hub segments: one warp per 256-entry task (the hub task table of the segment ordering) writes a partial, then one CTA per
+// hub adds the partials: thread-strided in ascending order, then a fixed tree over the CTA
 template <int HT>
-__global__ void __launch_bounds__(512)
-split_sum_hub_kernel(const int* __restrict__ segptr, const int* __restrict__ hub_seg, const int* __restrict__ idx,
-                     const float* __restrict__ dsv, int H, float* __restrict__ dst, long ldd, int qoff) {
-    __shared__ float red[HT][512];
-    const int seg = __ldg(hub_seg + blockIdx.x);
-    const int beg = __ldg(segptr + seg), end = __ldg(segptr + seg + 1);
+__global__ void __launch_bounds__(SPK_CTA_THREADS)
+split_sum_tasks_kernel(const HubTasks hub, const int* __restrict__ idx, const float* __restrict__ dsv, int H) {
+    const int lane = threadIdx.x & 31;
+    const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (task >= hub.n_tasks) return;
+    const int beg = __ldg(hub.task_beg + task), end = __ldg(hub.task_end + task);
     float u[HT];
 #pragma unroll
     for (int h = 0; h < HT; ++h) u[h] = 0.f;
-    for (int e = beg + threadIdx.x; e < end; e += 512) {
+    for (int e = beg + lane; e < end; e += 32) {
         const long p = idx ? (long)__ldg(idx + e) : (long)e;
 #pragma unroll
         for (int h = 0; h < HT; ++h)
             if (h < H) u[h] += __ldg(dsv + p * H + h);
     }
 #pragma unroll
+    for (int h = 0; h < HT; ++h) u[h] = warp_sum(u[h]);
+    if (lane < HT) hub.partial[(long)task * hub.ldpart + lane] = selh<HT>(lane, u);
+}
+
+template <int HT>
+__global__ void __launch_bounds__(256)
+split_sum_hub_kernel(const HubTasks hub, int H, float* __restrict__ dst, long ldd, int qoff) {
+    __shared__ float red[HT][256];
+    const int seg = __ldg(hub.hub_seg + blockIdx.x);
+    const int t0 = __ldg(hub.hub_task_ptr + blockIdx.x), t1 = __ldg(hub.hub_task_ptr + blockIdx.x + 1);
+    float u[HT];
+#pragma unroll
+    for (int h = 0; h < HT; ++h) u[h] = 0.f;
+    for (int t = t0 + threadIdx.x; t < t1; t += 256) {
+#pragma unroll
+        for (int h = 0; h < HT; ++h) u[h] += hub.partial[(long)t * hub.ldpart + h];
+    }
+#pragma unroll
     for (int h = 0; h < HT; ++h) red[h][threadIdx.x] = u[h];
     __syncthreads();
-    for (int s = 256; s > 0; s >>= 1) {
+    for (int s = 128; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) {
 #pragma unroll
             for (int h = 0; h < HT; ++h) red[h][threadIdx.x] += red[h][threadIdx.x + s];
@@ -344,41 +363,76 @@ int launch_sums(const int* segptr, const int* idx, const float* dsv, int H, int 
     const unsigned grid = (n_seg + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
     split_sum_kernel<HT><<<grid, SPK_CTA_THREADS, 0, s>>>(segptr, idx, dsv, H, n_seg, hub.hub_thresh, dst, ldd, qoff);
     if (int rc = check_launch("split_sum")) return rc;
-    if (hub.n_hubs > 0) {
-        split_sum_hub_kernel<HT><<<hub.n_hubs, 512, 0, s>>>(segptr, hub.hub_seg, idx, dsv, H, dst, ldd, qoff);
+    if (hub.n_tasks > 0) {
+        split_sum_tasks_kernel<HT><<<(hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA, SPK_CTA_THREADS, 0, s>>>(hub, idx, dsv, H);
+        if (int rc = check_launch("split_sum_tasks")) return rc;
+        split_sum_hub_kernel<HT><<<hub.n_hubs, 256, 0, s>>>(hub, H, dst, ldd, qoff);
         if (int rc = check_launch("split_sum_hub")) return rc;
     }
     return 0;
 }
 
+// tuning variants of the two gather passes (SPK_SPLIT_VARIANT): unroll depth U (row gathers in flight per warp) and CTAs/SM
+static int split_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_SPLIT_VARIANT"); v = e ? atoi(e) : 0; if (v < 0 || v > 3) v = 0; }
+    return v;
+}
+
+template <int NCH, int HT, int U, int MINB>
+int launch_split_passes(const BwdSplitArgs& a, cudaStream_t s, int which) {
+    if (which == 0) {
+        if (a.n_cols > 0) {
+            const unsigned grid = (a.n_cols + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+            split_cols_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+            if (int rc = check_launch("split_cols")) return rc;
+        }
+        if (a.col_hub.n_tasks > 0) {
+            const unsigned grid = (a.col_hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+            split_cols_tasks_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+            if (int rc = check_launch("split_cols_tasks")) return rc;
+        }
+    } else {
+        if (a.n_rel > 0) {
+            const unsigned grid = (a.n_rel + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+            split_rels_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+            if (int rc = check_launch("split_rels")) return rc;
+        }
+        if (a.rel_hub.n_tasks > 0) {
+            const unsigned grid = (a.rel_hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+            split_rels_tasks_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
+            if (int rc = check_launch("split_rels_tasks")) return rc;
+        }
+    }
+    return 0;
+}
+
+template <int NCH, int HT>
+int launch_split_pass(const BwdSplitArgs& a, cudaStream_t s, int which) {
+    if constexpr (NCH <= 2) {
+        switch (split_variant()) {
+            case 1: return launch_split_passes<NCH, HT, 4, 3>(a, s, which);
+            case 2: return launch_split_passes<NCH, HT, 2, 4>(a, s, which);
+            case 3: return launch_split_passes<NCH, HT, 8, 2>(a, s, which);
+            default: return launch_split_passes<NCH, HT, 4, 4>(a, s, which);   // 32 warps/SM measured best (10.4 vs 11.0 / 11.2 / 14.2 ms)
+        }
+    } else {
+        return launch_split_passes<NCH, HT, 2, 2>(a, s, which);
+    }
+}
+
 template <int NCH, int HT>
 int launch_split_t(const BwdSplitArgs& a, cudaStream_t s) {
-    constexpr int U = (NCH <= 2) ? 4 : 2;
-    constexpr int MINB = (NCH <= 2) ? 3 : 2;
     if (int rc = launch_edge_bwd_node(a.f, s)) return rc;
-    if (a.n_cols > 0) {
-        const unsigned grid = (a.n_cols + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        split_cols_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
-        if (int rc = check_launch("split_cols")) return rc;
-    }
+    if (int rc = launch_split_pass<NCH, HT>(a, s, 0)) return rc;
     if (a.col_hub.n_tasks > 0) {
-        const unsigned grid = (a.col_hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        split_cols_tasks_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
-        if (int rc = check_launch("split_cols_tasks")) return rc;
         SegGatherArgs fa;
         fa.segptr = a.colptr; fa.src = nullptr; fa.pos = nullptr; fa.G = a.G; fa.ldg = a.ldg; fa.rec = nullptr;
         fa.outp = a.dP2; fa.ldout = a.ldd2; fa.n_seg = a.n_cols; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.col_hub;
         if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
     }
-    if (a.n_rel > 0) {
-        const unsigned grid = (a.n_rel + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        split_rels_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
-        if (int rc = check_launch("split_rels")) return rc;
-    }
+    if (int rc = launch_split_pass<NCH, HT>(a, s, 1)) return rc;
     if (a.rel_hub.n_tasks > 0) {
-        const unsigned grid = (a.rel_hub.n_tasks + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
-        split_rels_tasks_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
-        if (int rc = check_launch("split_rels_tasks")) return rc;
         SegGatherArgs fa;
         fa.segptr = a.relptr; fa.src = nullptr; fa.pos = nullptr; fa.G = a.G; fa.ldg = a.ldg; fa.rec = nullptr;
         fa.outp = a.dP3; fa.ldout = a.ldd3; fa.n_seg = a.n_rel; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.rel_hub;

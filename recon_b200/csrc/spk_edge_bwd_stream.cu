@@ -79,7 +79,7 @@ __device__ __forceinline__ void prologue_smem(const EdgeBwdRowsArgs& a, long row
             if (a.apply_elu) {
                 const bool pos = o[k] > 0.f;
                 dh[k] = pos ? gg[k] : gg[k] * (o[k] + 1.f);
-                hv[k] = pos ? o[k] : (o[k] > -1.f ? log1pf(o[k]) : 0.f);
+                hv[k] = pos ? o[k] : (o[k] > -1.f ? fast_log1p(o[k]) : 0.f);
             } else {
                 dh[k] = gg[k];
                 hv[k] = o[k];

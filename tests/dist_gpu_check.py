@@ -27,7 +27,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     rank, world = dist.get_rank(), dist.get_world_size()
     n, e, r, f, d, h = 6000, 90000, 37, 50, 100, 2
-    edge, etype, nhop = make_kg(n, e, r, alpha=1.1, n_nhop=20000, seed=21)
+    n_nhop = int(os.environ.get("DIST_CHECK_NHOP", "20000"))       # 0: no 2-hop edges -> the split-dot backward runs
+    edge, etype, nhop = make_kg(n, e, r, alpha=1.1, n_nhop=n_nhop, seed=21)
     p = O.init_params(n, r, f, d, h, seed=21)
     gen = torch.Generator().manual_seed(22)
     g_ent, g_rel = torch.randn(n, d * h, generator=gen), torch.randn(r, d * h, generator=gen)
