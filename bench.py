@@ -315,10 +315,17 @@ class SingleGPU:
             "edge_attn_fwd": e * (4 * dt + 8) + 4 * self.e2 + n * (8 * dt),
             "edge_attn_bwd_rows": e * (4 * dt + 8 + 8 * h_avg) + 4 * self.e2 + n * (20 * dt),
             "edge_attn_bwd_segments:cols": e * (4 * dt + 8 + 8 * h_avg) + n * (4 * dt),
+            # split-dot backward of the projected layer (layer 2, H = 1): one C-ABI call = node pass + column pass +
+            # relation pass + sums; charged with SURVEY 8d's pass A + pass B bytes of that layer (the relation pass and
+            # the record traffic beyond 16 B/edge are not in B_alg)
+            "edge_attn_bwd_split": e * (8 * dt + 16 + 16 * 1) + n * (24 * dt),
         }
         cand = {}
-        for k, v in prof.items():                  # per-width tags (":w208") of the segment passes fold into one entry
-            base = k.rsplit(":w", 1)[0]
+        wd_proj = (dt + HEADS + 7) // 8 * 8          # table width of the projected path (208); narrower launches belong to
+        for k, v in prof.items():                  # the aggregate-then-project layer and move fewer bytes than B_alg charges
+            base, _, wtag = k.partition(":w") if ":w" in k else (k, "", "")
+            if wtag and int(wtag) != wd_proj:
+                continue
             if base in algs:
                 ms0, c0 = cand.get(base, (0.0, 0))
                 cand[base] = (ms0 + v[0], c0 + v[1])

@@ -272,10 +272,11 @@ struct IdxBatch { int col, t1, t2; float m[HT]; };
 // exp(x) = 2^(x*log2e): ex2.approx (2 ulp) + one rounding of the product; |rel err| <~ 1e-7 * (1 + |x|)
 __device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
 
-template <int NCH, int HT, bool HAS2, bool TASKS>
-__global__ void __launch_bounds__(STREAM_WARPS * 32, 2)
+// NGV / MINB: tuning variant (ring depth in groups, CTAs per SM); 0 = the StreamCfg default with 2 CTAs/SM
+template <int NCH, int HT, bool HAS2, bool TASKS, int NGV = 0, int MINB = 2>
+__global__ void __launch_bounds__(STREAM_WARPS * 32, MINB)
 edge_fwd_stream_kernel(const EdgeFwdArgs a) {
-    constexpr int G = STREAM_G, NG = StreamCfg<NCH, HAS2>::NG, S = G * NG;
+    constexpr int G = STREAM_G, NG = NGV ? NGV : StreamCfg<NCH, HAS2>::NG, S = G * NG;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const LayerGeom g = a.g;
@@ -489,10 +490,44 @@ edge_fwd_stream_kernel(const EdgeFwdArgs a) {
     if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(a.nanflag, 1);
 }
 
-template <int NCH, bool HAS2>
+template <int NCH, bool HAS2, int NGV = 0>
 static size_t stream_smem_bytes(const LayerGeom& g) {
     const size_t row_bytes = (size_t)g.Wd4 * 16;
-    return STREAM_WARPS * (StreamCfg<NCH, HAS2>::NG * STREAM_G * row_bytes * (HAS2 ? 3 : 2) + 2 * row_bytes + 128);
+    return STREAM_WARPS * ((NGV ? NGV : StreamCfg<NCH, HAS2>::NG) * STREAM_G * row_bytes * (HAS2 ? 3 : 2) + 2 * row_bytes + 128);
+}
+
+// SPK_FWD_VARIANT=1 (default, measured 4.23 vs 4.64 ms): ring of 2 groups (4 slots per warp) and 3 CTAs/SM; 0: 3 groups, 2 CTAs/SM
+static int fwd_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_FWD_VARIANT"); v = e ? atoi(e) : 1; if (v < 0 || v > 1) v = 1; }
+    return v;
+}
+
+template <int NCH, int HT, bool HAS2, int NGV, int MINB>
+static int launch_fwd_stream_v(const EdgeFwdArgs& a, cudaStream_t s) {
+    const size_t smem = stream_smem_bytes<NCH, HAS2, NGV>(a.g);
+    static size_t set_rows = 0, set_tasks = 0;
+    if (a.n_rows > 0) {
+        if (set_rows < smem) {
+            cudaFuncSetAttribute(edge_fwd_stream_kernel<NCH, HT, HAS2, false, NGV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            set_rows = smem;
+        }
+        const unsigned grid = (unsigned)((a.n_rows + 32L * STREAM_WARPS - 1) / (32L * STREAM_WARPS));
+        edge_fwd_stream_kernel<NCH, HT, HAS2, false, NGV, MINB><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
+        if (int rc = check_launch("edge_fwd_stream_rows")) return rc;
+    }
+    if (a.hub.n_tasks > 0) {
+        if (set_tasks < smem) {
+            cudaFuncSetAttribute(edge_fwd_stream_kernel<NCH, HT, HAS2, true, NGV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            set_tasks = smem;
+        }
+        const unsigned grid = (a.hub.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS;
+        edge_fwd_stream_kernel<NCH, HT, HAS2, true, NGV, MINB><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
+        if (int rc = check_launch("edge_fwd_stream_tasks")) return rc;
+        edge_fwd_hub_finalize_kernel<NCH, HT><<<a.hub.n_hubs, FinCfg<NCH>::NW * 32, 0, s>>>(a);
+        if (int rc = check_launch("edge_fwd_hub_finalize")) return rc;
+    }
+    return 0;
 }
 
 static bool use_stream() {
@@ -503,6 +538,7 @@ static bool use_stream() {
 
 template <int NCH, int HT, bool HAS2>
 static int launch_fwd_t(const EdgeFwdArgs& a, cudaStream_t s) {
+    if (use_stream() && NCH <= 2 && !HAS2 && fwd_variant() == 1) return launch_fwd_stream_v<NCH, HT, HAS2, 2, 3>(a, s);
     if (use_stream()) {
         const size_t smem = stream_smem_bytes<NCH, HAS2>(a.g);
         static size_t set_rows = 0, set_tasks = 0;

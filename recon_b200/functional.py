@@ -49,7 +49,7 @@ def extended_weights(a_list, a2_list, in_features, geom):
     for h, (a, a2) in enumerate(zip(a_list, a2_list)):
         lo = h * geom.Dp
         at = a.t()                                       # [2F+Rd, D]
-        qa = at.mm(a2.t()).squeeze(1)                    # [2F+Rd]  = a^T a_2^T
+        qa = (at * a2).sum(dim=1)                        # [2F+Rd]  = a^T a_2^T (elementwise: no library GEMV on the path)
         Wn[:, lo:lo + geom.D] = at[:F]
         Wn[:, geom.Dt + h] = qa[:F]
         Wn[:, geom.Wd + lo:geom.Wd + lo + geom.D] = at[F:2 * F]
@@ -439,7 +439,7 @@ def agg_weights(a_list, a2_list, geom):
     V3 = a0.new_zeros(Rd, 4)
     for h, (a, a2) in enumerate(zip(a_list, a2_list)):
         at = a.t()                                        # [2F+Rd, D]
-        qa = at.mm(a2.t()).squeeze(1)                     # a^T a_2^T
+        qa = (at * a2).sum(dim=1)                         # a^T a_2^T
         Wa[h, :F] = at[:F]
         Wa[h, Fp:Fp + F] = at[F:2 * F]
         Wa[h, 2 * Fp:2 * Fp + Rd] = at[2 * F:]
