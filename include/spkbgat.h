@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* spk_stream_t;              /* cudaStream_t */
 
-#define SPK_ABI_VERSION 2
+#define SPK_ABI_VERSION 3
 int spk_abi_version(void);
 const char* spk_last_error(void);
 int64_t spk_launch_count(void);          /* kernels launched through this library so far */
@@ -253,6 +253,44 @@ int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t
                           const float* inv_norm, float* dew, int64_t lde, float* dx2, int64_t ldx,
                           int64_t n_rows, int32_t width, spk_stream_t stream);
 int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream);
+
+/* ---- N1: the training step right after the hot path ----
+ * batch_gat_loss (GAT/main.py:344-376): `triples` int64 [T,3] = (head, relation, tail) rows, the first n_pos positive,
+ * the remaining T - n_pos = 2*ratio*n_pos corrupted (negative k pairs with positive k mod n_pos, main.py:351);
+ * x = ent[h] + rel[r] - ent[t], L1 norm, nn.MarginRankingLoss(margin) with y = -1 (main.py:367-372,451),
+ * mean != 0: mean over the pairs (the reference's reduction), else sum. Outputs: loss[1]; saved for backward:
+ * sgn uint32 [T, ceil(width/4)] (int8 sign(x) packed by 4) and coef float [T] (d loss / d norm of every triple).
+ * norm float [T] and partial double [spk_margin_loss_partials(n_pos)] are scratch. Out-of-range ids set *err_flag. */
+int64_t spk_margin_loss_partials(int64_t n_pos);
+int spk_margin_loss_fwd(const int64_t* triples, int64_t n_triples, int64_t n_pos,
+                        const float* ent, int64_t lde, int64_t n_ent, const float* rel, int64_t ldr, int64_t n_rel,
+                        int32_t width, float margin, int32_t mean,
+                        float* norm, uint32_t* sgn, float* coef, double* partial, float* loss,
+                        int32_t* err_flag, spk_stream_t stream);
+/* incidence lists for the backward: entity keys (2 per triple, value = 2*t + is_tail) and relation keys (value = t);
+ * sorted with spk_sort_pairs and cut into segments with spk_segment_ptr by the caller. */
+int spk_triple_incidence(const int64_t* triples, int64_t n_triples, int64_t n_ent, int64_t n_rel,
+                         int32_t* ent_keys /*[2T]*/, int32_t* ent_vals, int32_t* rel_keys /*[T]*/, int32_t* rel_vals,
+                         int32_t* err_flag, spk_stream_t stream);
+/* Backward of batch_gat_loss w.r.t. entity_embed (mode 0) or relation_embed (mode 1): replaces autograd's
+ * index_put_(accumulate) scatter. out[seg,:] = gscale[0] * sum over the segment's incidences, in list order, of
+ * (+-) coef[t] * sign(x_t)  (- for tails); rows without incidences are written as zeros (dense gradient, the form
+ * SpKBGATModified's backward consumes). Deterministic; hub segments through task partials [n_tasks, ldpart >= 4*ceil(width/4)]. */
+typedef struct {
+    const int32_t* segptr; const int32_t* inc;     /* [n_seg+1], sorted incidence values */
+    const float* coef; const uint32_t* sgn;        /* from spk_margin_loss_fwd */
+    const float* gscale;                           /* [1] upstream gradient of the scalar loss (device) */
+    float* out; int64_t ldo;                       /* [n_seg, width] */
+    int32_t n_seg; int32_t width; int32_t mode; int32_t reserved;
+    spk_hub_tasks hub;
+} spk_loss_bwd_args;
+int spk_margin_loss_bwd(const spk_loss_bwd_args* args, spk_stream_t stream);
+/* optimizer.step() of torch.optim.SGD(lr) (main.py:445-446,524): param[i] -= lr * grad[i], up to 16 tensors per launch */
+typedef struct {
+    float* param[16]; const float* grad[16]; int64_t numel[16];
+    int32_t count; float lr;
+} spk_sgd_args;
+int spk_sgd_step(const spk_sgd_args* args, spk_stream_t stream);
 
 #ifdef __cplusplus
 }

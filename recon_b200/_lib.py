@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f32p = C.POINTER(C.c_float)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Geom(C.Structure):
@@ -116,6 +116,18 @@ class AggBwdArgs(C.Structure):
 
 _VP, _I64, _I32 = C.c_void_p, C.c_int64, C.c_int32
 
+class LossBwdArgs(C.Structure):
+    _fields_ = [("segptr", C.c_void_p), ("inc", C.c_void_p), ("coef", C.c_void_p), ("sgn", C.c_void_p),
+                ("gscale", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int64),
+                ("n_seg", C.c_int32), ("width", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32),
+                ("hub", HubTasks)]
+
+
+class SgdArgs(C.Structure):
+    _fields_ = [("param", C.c_void_p * 16), ("grad", C.c_void_p * 16), ("numel", C.c_int64 * 16),
+                ("count", C.c_int32), ("lr", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/spkbgat.h declares
 SIGNATURES = {
     "spk_abi_version": (_I32, []),
@@ -155,6 +167,12 @@ SIGNATURES = {
     "spk_residual_norm_fwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
     "spk_residual_norm_bwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP]),
     "spk_mask_from_index": (_I32, [_VP, _I64, _VP, _I64, _VP]),
+    "spk_margin_loss_partials": (_I64, [_I64]),
+    "spk_margin_loss_fwd": (_I32, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64, _I32, C.c_float, _I32,
+                                   _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "spk_triple_incidence": (_I32, [_VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "spk_margin_loss_bwd": (_I32, [C.POINTER(LossBwdArgs), _VP]),
+    "spk_sgd_step": (_I32, [C.POINTER(SgdArgs), _VP]),
 }
 
 _lib = None

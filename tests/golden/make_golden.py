@@ -165,6 +165,48 @@ def edges_case(name, n, t, r, seed, batch_size, partial=False):
     print(name, "ok", adj_idx.shape, nhop.shape, fnhop.shape)
 
 
+def _reference_function(path, name, env):
+    """Compile ONE top-level function of a reference file from its own source text (read here, never copied into the
+    repo) into `env`. GAT/main.py cannot be imported: it parses sys.argv and imports matplotlib at module level."""
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+    exec(code, env)
+    return env[name]
+
+
+def loss_case(name, n_ent, n_rel, width, n_pos, ratio, margin, seed, hub_share=0.0):
+    """batch_gat_loss of GAT/main.py:344-376 (unmodified function text) + loss.backward() + one SGD step."""
+    from oracle.loss import make_train_indices
+    env = {"torch": torch, "CUDA": False, "int": int,
+           "args": types.SimpleNamespace(valid_invalid_ratio_gat=ratio)}
+    ref_loss = _reference_function("/root/reference/GAT/main.py", "batch_gat_loss", env)
+    gen = torch.Generator().manual_seed(seed)
+    tri = make_train_indices(n_ent, n_rel, n_pos, ratio, seed + 1, hub_entity=3, hub_share=hub_share)
+    out = {"train_indices": tri, "ratio": np.int32(ratio), "margin": np.float32(margin)}
+    ent0 = torch.randn(n_ent, width, generator=gen); rel0 = torch.randn(n_rel, width, generator=gen)
+    ent0 = torch.nn.functional.normalize(ent0, p=2, dim=1)        # the hot path's outputs are unit rows (models.py:179)
+    tri[0, 0], tri[0, 2] = 6, 5                                   # x of triple 0 has exact zeros: sign(0) = 0 in the backward
+    hw, r0 = width // 2, int(tri[0, 1])                           # (dyadic values: the sum is exact in fp32 AND fp64)
+    ent0[6, :hw] = torch.round(ent0[6, :hw] * 1024) / 1024
+    rel0[r0, :hw] = torch.round(rel0[r0, :hw] * 1024) / 1024
+    ent0[5, :hw] = ent0[6, :hw] + rel0[r0, :hw]
+    out["entity_embed"], out["relation_embed"] = ent0, rel0
+    lr = 1e-3
+    for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        ent = ent0.to(dt).clone().requires_grad_(True); rel = rel0.to(dt).clone().requires_grad_(True)
+        loss = ref_loss(torch.nn.MarginRankingLoss(margin=margin), tri, ent, rel)
+        loss.backward()
+        out[f"{tag}.loss"] = loss.detach(); out[f"{tag}.grad.entity_embed"] = ent.grad; out[f"{tag}.grad.relation_embed"] = rel.grad
+        opt = torch.optim.SGD([ent, rel], lr=lr)                   # main.py:445-446
+        opt.step()
+        out[f"{tag}.sgd.entity_embed"] = ent.detach().clone(); out[f"{tag}.sgd.relation_embed"] = rel.detach().clone()
+    out["lr"] = np.float64(lr)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v) for k, v in out.items()})
+    print(name, "ok", float(out["f32.loss"]), tuple(tri.shape))
+
+
 if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore")
@@ -181,6 +223,9 @@ if __name__ == "__main__":
     edges_case("edges_a", 40, 160, 5, 30, 12)
     edges_case("edges_b", 25, 200, 3, 31, 25)
     edges_case("edges_partial", 40, 160, 5, 32, 15, partial=True)
+    loss_case("loss_small", 40, 5, 12, 30, 2, 0.5, 40)
+    loss_case("loss_refdims_hub", 300, 11, 200, 700, 2, 5.0, 41, hub_share=0.9)     # entity 3 heads ~630 positives: hub segment
+    loss_case("loss_ratio3_oddwidth", 50, 4, 7, 25, 3, 1.0, 42)
     # the hand-checked toy KG of SURVEY.md 3.4
     toy = np.array([(0, 5, 1), (0, 6, 1), (0, 7, 2), (1, 8, 3), (2, 9, 3), (2, 4, 2), (3, 1, 4), (1, 2, 0)])
     np.savez_compressed(os.path.join(HERE, "edges_toy.npz"), triples=toy)
