@@ -292,6 +292,15 @@ typedef struct {
 } spk_sgd_args;
 int spk_sgd_step(const spk_sgd_args* args, spk_stream_t stream);
 
+/* ---- N2: the embedding wire format the downstream half of RECON reads. HOST pointers, no GPU work. ----
+ * spk_export_json writes byte-for-byte what save_embed (GAT/main.py:406-413) writes with
+ * json.dump({idx: row.tolist()}, f, indent=4, cls=CustomEncoder): keys "0".."rows-1", one float per line formatted like
+ * Python's repr of the float32 widened to double; rows are formatted by n_threads host threads (0 = all cores).
+ * spk_export_bin writes the side-car: 64-byte header {"SPKEMB01", int64 rows, int64 width, int64 dtype = 0 (fp32 LE)}
+ * followed by rows*width fp32 row-major. */
+int spk_export_json(const float* host_rows, int64_t rows, int64_t width, int64_t ld, const char* path, int32_t n_threads);
+int spk_export_bin(const float* host_rows, int64_t rows, int64_t width, int64_t ld, const char* path);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,174 @@
+// N2: the wire format the second half of RECON reads.
+//   save_embed (GAT/main.py:406-413) writes  json.dump({idx: row.tolist()}, f, indent=4, cls=CustomEncoder)
+//   and the consumer does json.load + gat_embeddings["<idx>"] (train.py:100-130, utils/context_utils.py:444-504).
+// For the C2 table (2M x 200 floats) that is ~10 GB of text produced by a pure-Python encoder; this file emits the
+// byte-identical text from a host fp32 buffer with all cores (rows formatted in parallel, written in order), plus a
+// binary side-car (header + raw fp32 rows) for consumers that can mmap.
+//
+// Byte-identical means Python's float repr of the float32 value widened to double (ndarray.tolist()):
+//   shortest digit string that round-trips the double (std::to_chars == David Gay's mode 0), fixed notation when
+//   -4 < decpt <= 16 with ".0" for integral values, else d[.ddd]e[+-]XX with at least two exponent digits
+//   (CPython Python/pystrtod.c format_float_short, type 'r'); NaN / Infinity / -Infinity as json emits them.
+#include "../../include/spkbgat.h"
+
+#include <algorithm>
+#include <charconv>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace spk {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+// appends repr(float(v)) to out
+inline void append_pyfloat(std::string& out, float f) {
+    const double v = (double)f;
+    if (std::isnan(v)) { out += "NaN"; return; }
+    if (std::isinf(v)) { out += v > 0 ? "Infinity" : "-Infinity"; return; }
+    if (v == 0.0) { out += std::signbit(v) ? "-0.0" : "0.0"; return; }
+    char buf[40];
+    const auto res = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    // buf = [-]d[.ddd]e[+-]XX
+    const char* p = buf;
+    if (*p == '-') { out += '-'; ++p; }
+    char digits[24];
+    int nd = 0;
+    digits[nd++] = *p++;
+    if (*p == '.') {
+        ++p;
+        while (*p != 'e') digits[nd++] = *p++;
+    }
+    ++p;                                      // 'e'
+    int esign = 1;
+    if (*p == '-') { esign = -1; ++p; } else if (*p == '+') { ++p; }
+    int ex = 0;
+    while (p < res.ptr) ex = ex * 10 + (*p++ - '0');
+    const int decpt = esign * ex + 1;         // value = 0.d1d2... x 10^decpt
+    if (decpt <= -4 || decpt > 16) {          // exponent notation
+        out += digits[0];
+        if (nd > 1) { out += '.'; out.append(digits + 1, nd - 1); }
+        int e10 = decpt - 1;
+        out += 'e';
+        out += e10 < 0 ? '-' : '+';
+        e10 = e10 < 0 ? -e10 : e10;
+        char eb[8];
+        int n = 0;
+        do { eb[n++] = (char)('0' + e10 % 10); e10 /= 10; } while (e10);
+        if (n < 2) eb[n++] = '0';
+        while (n) out += eb[--n];
+    } else if (decpt <= 0) {
+        out += "0.";
+        out.append((size_t)(-decpt), '0');
+        out.append(digits, nd);
+    } else if (decpt >= nd) {
+        out.append(digits, nd);
+        out.append((size_t)(decpt - nd), '0');
+        out += ".0";
+    } else {
+        out.append(digits, decpt);
+        out += '.';
+        out.append(digits + decpt, nd - decpt);
+    }
+}
+
+// rows [r0, r1) of the dict body:  "<idx>": [\n        v,\n        v\n    ]  joined by ",\n    "
+void format_rows(const float* data, int64_t ld, int64_t width, int64_t r0, int64_t r1, int64_t n_rows, std::string& out) {
+    out.clear();
+    out.reserve((size_t)((r1 - r0) * (width * 30 + 32)));
+    char kb[32];
+    for (int64_t r = r0; r < r1; ++r) {
+        out += "\n    \"";
+        const int kn = snprintf(kb, sizeof(kb), "%lld", (long long)r);
+        out.append(kb, kn);
+        out += "\": [";
+        if (width == 0) {
+            out += "]";
+        } else {
+            const float* row = data + r * ld;
+            for (int64_t c = 0; c < width; ++c) {
+                out += "\n        ";
+                append_pyfloat(out, row[c]);
+                if (c + 1 < width) out += ',';
+            }
+            out += "\n    ]";
+        }
+        if (r + 1 < n_rows) out += ',';
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int spk_export_json(const float* host, int64_t rows, int64_t width, int64_t ld, const char* path, int32_t n_threads) {
+    if (rows < 0 || width < 0 || (rows > 0 && width > 0 && host == nullptr) || ld < width || path == nullptr) {
+        spk::set_error("export_json: bad arguments (rows=%lld width=%lld ld=%lld)", (long long)rows, (long long)width, (long long)ld);
+        return 2;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) { spk::set_error("export_json: cannot open %s", path); return 3; }
+    int rc = 0;
+    if (rows == 0) {
+        if (fputs("{}", f) < 0) rc = 4;
+    } else {
+        int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+        nt = std::max(1, std::min(nt, 256));
+        const int64_t block = std::max<int64_t>(1, (int64_t)(4 << 20) / std::max<int64_t>(1, width * 26));   // ~4 MB of text per task
+        const int64_t wave = block * nt;
+        std::vector<std::string> bufs((size_t)nt);
+        if (fputc('{', f) == EOF) rc = 4;
+        for (int64_t w0 = 0; w0 < rows && rc == 0; w0 += wave) {
+            std::vector<std::thread> th;
+            int used = 0;
+            for (int t = 0; t < nt; ++t) {
+                const int64_t r0 = w0 + t * block, r1 = std::min(rows, r0 + block);
+                if (r0 >= rows) break;
+                ++used;
+                if (nt == 1) format_rows(host, ld, width, r0, r1, rows, bufs[t]);
+                else th.emplace_back(format_rows, host, ld, width, r0, r1, rows, std::ref(bufs[(size_t)t]));
+            }
+            for (auto& x : th) x.join();
+            for (int t = 0; t < used && rc == 0; ++t)
+                if (fwrite(bufs[t].data(), 1, bufs[t].size(), f) != bufs[t].size()) rc = 4;
+        }
+        if (rc == 0 && fputs("\n}", f) < 0) rc = 4;
+    }
+    if (fclose(f) != 0 && rc == 0) rc = 4;
+    if (rc) spk::set_error("export_json: write to %s failed", path);
+    return rc;
+}
+
+/* side-car: 64-byte header {magic "SPKEMB01", int64 rows, int64 width, int64 dtype(0 = fp32 LE), zero pad} + rows*width fp32 */
+int spk_export_bin(const float* host, int64_t rows, int64_t width, int64_t ld, const char* path) {
+    if (rows < 0 || width < 0 || (rows > 0 && width > 0 && host == nullptr) || ld < width || path == nullptr) {
+        spk::set_error("export_bin: bad arguments");
+        return 2;
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) { spk::set_error("export_bin: cannot open %s", path); return 3; }
+    char hdr[64];
+    memset(hdr, 0, sizeof(hdr));
+    memcpy(hdr, "SPKEMB01", 8);
+    const int64_t meta[3] = {rows, width, 0};
+    memcpy(hdr + 8, meta, sizeof(meta));
+    int rc = fwrite(hdr, 1, sizeof(hdr), f) == sizeof(hdr) ? 0 : 4;
+    if (rc == 0 && rows > 0 && width > 0) {
+        if (ld == width) {
+            if (fwrite(host, sizeof(float), (size_t)(rows * width), f) != (size_t)(rows * width)) rc = 4;
+        } else {
+            for (int64_t r = 0; r < rows && rc == 0; ++r)
+                if (fwrite(host + r * ld, sizeof(float), (size_t)width, f) != (size_t)width) rc = 4;
+        }
+    }
+    if (fclose(f) != 0 && rc == 0) rc = 4;
+    if (rc) spk::set_error("export_bin: write to %s failed", path);
+    return rc;
+}
+
+}  // extern "C"

@@ -132,12 +132,13 @@ def sgd_step(params, lr):
     for p in todo:
         if not p.is_cuda:
             raise RuntimeError("recon_b200 ops need CUDA tensors (no CPU fallback)")
-        if not (p.is_contiguous() and p.grad.is_contiguous() and p.dtype == torch.float32 and p.grad.dtype == torch.float32):
-            raise RuntimeError("sgd_step needs contiguous fp32 parameters and gradients")
+        if not (p.is_contiguous() and p.dtype == torch.float32 and p.grad.dtype == torch.float32):
+            raise RuntimeError("sgd_step needs contiguous fp32 parameters")
     for i in range(0, len(todo), 16):
         chunk = todo[i:i + 16]
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in chunk]
         a = _lib.SgdArgs()
-        for j, p in enumerate(chunk):
-            a.param[j] = p.data_ptr(); a.grad[j] = p.grad.data_ptr(); a.numel[j] = p.numel()
+        for j, (p, g) in enumerate(zip(chunk, grads)):
+            a.param[j] = p.data_ptr(); a.grad[j] = g.data_ptr(); a.numel[j] = p.numel()
         a.count = len(chunk); a.lr = float(lr)
         _lib.check(lib.spk_sgd_step(a, _lib.stream_ptr()), "sgd_step")

@@ -176,6 +176,40 @@ def _reference_function(path, name, env):
     return env[name]
 
 
+def _reference_class(path, name, env):
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == name)
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), env)
+    return env[name]
+
+
+def export_table(seed, rows, width):
+    """Rows of floats that exercise every branch of Python's float repr: hot-path-like unit rows, exponent-notation
+    boundaries (1e-4 / 1e-5, 1e16), integral values, denormals, +-0, NaN, +-Infinity."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.nn.functional.normalize(torch.randn(rows, width, generator=g), dim=1)
+    special = torch.tensor([0.0, -0.0, 1.0, -1.0, 100.0, 1e-4, 1e-5, 9.999e-5, 1.5e-5, 1e16, 1.5e16, 9.99e15, 1e15,
+                            123456.0, 16777216.0, 3.4028235e38, -3.4028235e38, 1.17549435e-38, 1e-45, 7e-42, 0.1, 0.5,
+                            2.5e-7, float("nan"), float("inf"), float("-inf"), 1e22, 1e-10, 4.0e9, 65504.0])
+    k = min(special.numel(), t.numel() - 1)
+    t.view(-1)[1:1 + k] = special[:k]
+    return t
+
+
+def export_case(name, seed, rows, width):
+    """save_embed of GAT/main.py:406-413 with its CustomEncoder (main.py:127-144), both executed from the reference's text."""
+    import json
+    import datetime
+    env = {"json": json, "np": np, "datetime": datetime}
+    _reference_class("/root/reference/GAT/main.py", "CustomEncoder", env)
+    ref_save = _reference_function("/root/reference/GAT/main.py", "save_embed", env)
+    t = export_table(seed, rows, width)
+    np.save(os.path.join(HERE, name + ".npy"), t.numpy())
+    ref_save(t, os.path.join(HERE, name + ".json"))
+    print(name, "ok", os.path.getsize(os.path.join(HERE, name + ".json")), "bytes")
+
+
 def loss_case(name, n_ent, n_rel, width, n_pos, ratio, margin, seed, hub_share=0.0):
     """batch_gat_loss of GAT/main.py:344-376 (unmodified function text) + loss.backward() + one SGD step."""
     from oracle.loss import make_train_indices
@@ -226,6 +260,8 @@ if __name__ == "__main__":
     loss_case("loss_small", 40, 5, 12, 30, 2, 0.5, 40)
     loss_case("loss_refdims_hub", 300, 11, 200, 700, 2, 5.0, 41, hub_share=0.9)     # entity 3 heads ~630 positives: hub segment
     loss_case("loss_ratio3_oddwidth", 50, 4, 7, 25, 3, 1.0, 42)
+    export_case("export_small", 50, 9, 7)
+    export_case("export_w200", 51, 3, 200)
     # the hand-checked toy KG of SURVEY.md 3.4
     toy = np.array([(0, 5, 1), (0, 6, 1), (0, 7, 2), (1, 8, 3), (2, 9, 3), (2, 4, 2), (3, 1, 4), (1, 2, 0)])
     np.savez_compressed(os.path.join(HERE, "edges_toy.npz"), triples=toy)
