@@ -301,6 +301,20 @@ int spk_sgd_step(const spk_sgd_args* args, spk_stream_t stream);
 int spk_export_json(const float* host_rows, int64_t rows, int64_t width, int64_t ld, const char* path, int32_t n_threads);
 int spk_export_bin(const float* host_rows, int64_t rows, int64_t width, int64_t ld, const char* path);
 
+/* ---- N3: Corpus.get_iteration_triples_batch (GAT/create_batch.py:262-351) on the device ----
+ * spk_triple_keys: key[i] = (h*R + r)*N + t of triples int64 [M,3]; pass the triples in (h, r, t) lexicographic order to
+ * get the sorted membership array that stands in for valid_triples_dict (create_batch.py:82-83).
+ * spk_corrupt_triples: out_indices int64 [(2*ratio+1)*P, 3], out_values float [(2*ratio+1)*P]: the P positives, then
+ * 2*ratio tiled copies of which [0, P*(ratio/2)) get a corrupted head, the next P*(ratio/2) a corrupted tail, rows from
+ * P*ratio on a corrupted relation (value -1; see the layout in csrc/spk_sampler.cu). init_entities / init_relations
+ * (int64 [P*ratio], may be null) are the first candidates, exactly the reference's random_entities / random_relations;
+ * a candidate that makes a valid triple is redrawn from a counter-based generator keyed on (seed, slot, attempt). */
+int spk_triple_keys(const int64_t* triples, int64_t n_triples, int64_t n_ent, int64_t n_rel, int64_t* keys,
+                    int32_t* err_flag, spk_stream_t stream);
+int spk_corrupt_triples(const int64_t* positives, int64_t n_pos, int32_t ratio, const int64_t* valid_keys, int64_t n_valid,
+                        int64_t n_ent, int64_t n_rel, const int64_t* init_entities, const int64_t* init_relations,
+                        uint64_t seed, int64_t* out_indices, float* out_values, spk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

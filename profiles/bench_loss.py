@@ -2,8 +2,9 @@
 Workload: the hot path's C2 output tables (2M x 200 entity rows, 1k x 200 relation rows), P positives with
 valid_invalid_ratio_gat = 2 (main.py:68-69) -> T = 5 P triples. Prints one JSON line.
   python profiles/bench_loss.py [--pos 2000000] [--steps 10]
-Algorithmic bytes: forward T * (3 * 4 * width) row gathers + T * (24 + width) (ids in, packed signs out);
-backward 3 T incidences * (width + 8) + (N + R) * 4 * width dense gradient rows."""
+Algorithmic bytes: forward T * (2 * 4 * width) entity-row gathers (the R x width relation table is
+cache-resident) + T * (24 + width + 8) (ids in, packed signs + norm / coef out); backward 3 T incidences * (width + 8)
++ (N + R) * 4 * width dense gradient rows."""
 import argparse
 import json
 import os
@@ -48,7 +49,7 @@ def main():
         if i >= 3:
             tf += ev[0].elapsed_time(ev[1]); tb += ev[1].elapsed_time(ev[2]); ts += ev[2].elapsed_time(ev[3])
     k = args.steps
-    fwd_b = t * (3 * 4 * w) + t * (24 + w)
+    fwd_b = t * (2 * 4 * w) + t * (24 + w + 8)
     bwd_b = 3 * t * (w + 8) + (n + r) * 4 * w
     sgd_b = (n + r) * w * 12
     print(json.dumps({"workload": f"loss: N={n} R={r} width={w} P={p} T={t}", "loss": float(loss),

@@ -173,6 +173,8 @@ SIGNATURES = {
     "spk_triple_incidence": (_I32, [_VP, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "spk_margin_loss_bwd": (_I32, [C.POINTER(LossBwdArgs), _VP]),
     "spk_sgd_step": (_I32, [C.POINTER(SgdArgs), _VP]),
+    "spk_triple_keys": (_I32, [_VP, _I64, _I64, _I64, _VP, _VP, _VP]),
+    "spk_corrupt_triples": (_I32, [_VP, _I64, _I32, _VP, _I64, _I64, _I64, _VP, _VP, C.c_uint64, _VP, _VP, _VP]),
     "spk_export_json": (_I32, [_VP, _I64, _I64, _I64, C.c_char_p, _I32]),
     "spk_export_bin": (_I32, [_VP, _I64, _I64, _I64, C.c_char_p]),
 }

@@ -176,6 +176,32 @@ def _reference_function(path, name, env):
     return env[name]
 
 
+def sampler_case(name, n, t, r, seed, batch_size, ratio, np_seed):
+    """Corpus.get_iteration_triples_batch (create_batch.py:262-351), the reference's own method, np.random seeded."""
+    triples = make_triples(n, t, r, seed)
+    rows = triples[:, 2].tolist(); cols = triples[:, 0].tolist(); data = triples[:, 1].tolist()
+    c = ref_batch.Corpus.__new__(ref_batch.Corpus)
+    c.train_adj_matrix = (torch.LongTensor([rows, cols]), torch.LongTensor(data))     # create_batch.py:28-31
+    c.graph = c.get_graph(Train=True)
+    c.node_neighbors_1hop = c.get_further_neighbors(nbd_size=1, Train=True)
+    c.entity2id = {str(i): i for i in range(n)}
+    c.relation2id = {str(i): i for i in range(r)}
+    c.invalid_valid_ratio = ratio
+    train_triples = [tuple(int(v) for v in row) for row in triples.tolist()]
+    c.valid_triples_dict = {j: i for i, j in enumerate(train_triples)}                # create_batch.py:82-83
+    gen = torch.Generator().manual_seed(seed + 7)
+    batch = torch.randperm(n, generator=gen)[:batch_size].tolist()
+    np.random.seed(np_seed)
+    idx, val = c.get_iteration_triples_batch(batch)
+    p = idx.shape[0] // (2 * ratio + 1)
+    np.random.seed(np_seed)                                  # replay the seed: the first draws the method made
+    init_e = np.random.randint(0, n, p * ratio); init_r = np.random.randint(0, r, p * ratio)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), triples=triples.numpy(), batch=np.asarray(batch),
+                        ratio=np.int32(ratio), np_seed=np.int64(np_seed), batch_indices=idx.copy(), batch_values=val.copy(),
+                        init_entities=init_e, init_relations=init_r, n_entities=np.int64(n), n_relations=np.int64(r))
+    print(name, "ok", idx.shape, "positives", p)
+
+
 def _reference_class(path, name, env):
     import ast
     src = open(path).read()
@@ -260,6 +286,10 @@ if __name__ == "__main__":
     loss_case("loss_small", 40, 5, 12, 30, 2, 0.5, 40)
     loss_case("loss_refdims_hub", 300, 11, 200, 700, 2, 5.0, 41, hub_share=0.9)     # entity 3 heads ~630 positives: hub segment
     loss_case("loss_ratio3_oddwidth", 50, 4, 7, 25, 3, 1.0, 42)
+    sampler_case("sampler_a", 60, 400, 6, 60, 20, 2, 123)
+    sampler_case("sampler_dense_r1", 12, 120, 1, 61, 12, 2, 124)      # one relation: relation corruption exhausts (348-350)
+    sampler_case("sampler_ratio3", 40, 200, 4, 62, 15, 3, 125)        # odd ratio: untouched +1 copies in the middle
+    sampler_case("sampler_ratio1", 40, 200, 4, 63, 15, 1, 126)        # ratio // 2 == 0: relation corruption only
     export_case("export_small", 50, 9, 7)
     export_case("export_w200", 51, 3, 200)
     # the hand-checked toy KG of SURVEY.md 3.4
