@@ -43,8 +43,9 @@ def sgd_step(params, grads, lr):
 
 
 def make_train_indices(n_ent, n_rel, n_pos, ratio, seed, hub_entity=None, hub_share=0.0):
-    """Synthetic [P positives ; ratio*P head-corrupted ; ratio*P tail-corrupted] rows in the layout
-    Corpus.get_iteration_triples_batch emits (create_batch.py:262-351): positives first, then their corruptions.
+    """Synthetic train_indices with the one property batch_gat_loss relies on (main.py:348-351): P positives first, then
+    2*ratio*P corrupted rows where row P + k corrupts positive k mod P (here: the first ratio*P rows get a random head,
+    the rest a random tail; the reference's sampler, oracle/sampler.py, also corrupts relations).
     hub_entity / hub_share force one entity into that share of the heads (long incidence segment)."""
     g = torch.Generator().manual_seed(seed)
     pos = torch.stack((torch.randint(0, n_ent, (n_pos,), generator=g), torch.randint(0, n_rel, (n_pos,), generator=g),
