@@ -2,6 +2,8 @@
 
 Drop-in for the reference's `GAT/layers.py` + `GAT/models.py` module surface:
     from recon_b200 import SpKBGATModified, SpGAT, SpGraphAttentionLayer, SpecialSpmmFunctionFinal, ConvKB
+The steps right after the hot path live in `recon_b200.loss` (batch_gat_loss, sgd_step),
+`recon_b200.export` (save_embed, load_embed, save_model) and `recon_b200.sampler` (TripleSampler).
 All compute runs in libspkbgat.so (hand-written CUDA behind the C ABI of include/spkbgat.h);
 there is no CPU or PyTorch-eager fallback.
 """

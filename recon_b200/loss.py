@@ -38,7 +38,7 @@ class TripleIncidence:
         self.rel_ptr = _segment_ptr(rk, n_rel)
         self.ent_hubs = HubSet(self.ent_ptr)
         self.rel_hubs = HubSet(self.rel_ptr)
-        self.err = err
+        # (ids were range-checked by spk_margin_loss_fwd before any backward can run; err stays 0 here)
 
 
 def _loss_backward(segptr, inc, hubs, coef, sgn, gscale, n_seg, width, mode):
