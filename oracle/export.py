@@ -30,6 +30,6 @@ class CustomEncoder(json.JSONEncoder):                       # main.py:127-144
 def save_embed(embeddings, save_path):                       # main.py:406-413
     emb_data = {}
     for idx in range(embeddings.shape[0]):
-        emb_data[idx] = np.array(embeddings[idx].cpu().detach())
+        emb_data[idx] = embeddings[idx].cpu().detach().numpy()      # np.array(tensor) in the reference: same values
     with open(save_path, "w") as f:
         json.dump(emb_data, f, indent=4, cls=CustomEncoder)
