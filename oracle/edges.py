@@ -16,12 +16,16 @@ Pinned against the reference's Corpus run in the build container
 from collections import deque
 
 
-def triples_to_adj(triples):
-    """triples: iterable of (head, rel, tail) ids in file order (directed=True).
-    Returns rows=[tail...], cols=[head...], data=[rel...] (preprocess.py:78-84)."""
+def triples_to_adj(triples, is_unweigted=False, directed=True):
+    """triples: iterable of (head, rel, tail) ids in file order.
+    Returns rows=[tail...], cols=[head...], data=[rel...] (preprocess.py:60-84); directed=False appends the
+    reversed edge (rows=head, cols=tail) before each edge (preprocess.py:66-73), is_unweigted stores 1 as data."""
     rows, cols, data = [], [], []
     for h, r, t in triples:
-        rows.append(int(t)); cols.append(int(h)); data.append(int(r))
+        d = 1 if is_unweigted else int(r)
+        if not directed:
+            rows.append(int(h)); cols.append(int(t)); data.append(d)
+        rows.append(int(t)); cols.append(int(h)); data.append(d)
     return rows, cols, data
 
 

@@ -7,10 +7,10 @@ The steps right after the hot path live in `recon_b200.loss` (bat
 All compute runs in libspkbgat.so (hand-written CUDA behind the C ABI of include/spkbgat.h);
 there is no CPU or PyTorch-eager fallback.
 """
-from .graph import KGraph                                                   # noqa: F401
+from .graph import KGraph, triples_to_adj                                                   # noqa: F401
 from .layers import (SpecialSpmmFunctionFinal, SpecialSpmmFinal,           # noqa: F401
                      SpGraphAttentionLayer, ConvKB)
 from .models import SpGAT, SpKBGATModified                                  # noqa: F401
 
-__all__ = ["KGraph", "SpecialSpmmFunctionFinal", "SpecialSpmmFinal", "SpGraphAttentionLayer", "ConvKB",
+__all__ = ["KGraph", "triples_to_adj", "SpecialSpmmFunctionFinal", "SpecialSpmmFinal", "SpGraphAttentionLayer", "ConvKB",
            "SpGAT", "SpKBGATModified"]

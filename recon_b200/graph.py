@@ -66,6 +66,22 @@ class HubSet:
             hub.partial = partial.data_ptr() if partial is not None else None; hub.ldpart = ldpart
 
 
+def triples_to_adj(triples, is_unweigted=False, directed=True):
+    """(head, rel, tail) id rows in file order -> the adjacency tensors the reference feeds the model:
+    `preprocess.load_data` (GAT/preprocess.py:48-87) + `Corpus.__init__` (GAT/create_batch.py:28-31), i.e.
+    edge_list = [rows = tail; cols = head] (the tail aggregates from the head), edge_type = relation id (1 when
+    is_unweigted); directed=False puts the reversed edge (rows = head, cols = tail) in front of every edge, as the
+    reference's append order does. Pure index glue on whatever device `triples` lives on."""
+    tr = torch.as_tensor(triples).to(torch.int64).reshape(-1, 3)
+    h, r, t = tr[:, 0], tr[:, 1], tr[:, 2]
+    val = torch.ones_like(r) if is_unweigted else r
+    if directed:
+        return torch.stack((t, h), dim=0).contiguous(), val.contiguous()
+    rows = torch.stack((h, t), dim=1).reshape(-1)            # reversed edge first, then the edge itself (preprocess.py:66-82)
+    cols = torch.stack((t, h), dim=1).reshape(-1)
+    return torch.stack((rows, cols), dim=0).contiguous(), torch.stack((val, val), dim=1).reshape(-1).contiguous()
+
+
 def _key_bits(n):
     return max(1, int(n - 1).bit_length()) if n > 1 else 1
 

@@ -176,6 +176,26 @@ def _reference_function(path, name, env):
     return env[name]
 
 
+def load_data_case(name, n, t, r, seed):
+    """preprocess.load_data (GAT/preprocess.py:48-87) on a temporary triple file, all four flag combinations."""
+    import tempfile
+    import preprocess as ref_pre
+    triples = make_triples(n, t, r, seed)
+    d = tempfile.mkdtemp()
+    fn = os.path.join(d, "train.txt")
+    e2i = {f"e{i}": i for i in range(n)}; r2i = {f"r{i}": i for i in range(r)}
+    with open(fn, "w") as f:
+        f.write("\n".join(f"e{h} r{k} e{tl}" for h, k, tl in triples.tolist()) + "\n\n")
+    out = {"triples": triples.numpy()}
+    for directed in (True, False):
+        for unw in (False, True):
+            td, (rows, cols, data), _ = ref_pre.load_data(fn, e2i, r2i, unw, directed)
+            assert td == [tuple(x) for x in triples.tolist()]
+            out[f"adj.directed{int(directed)}.unweighted{int(unw)}"] = np.asarray([rows, cols, data], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "ok")
+
+
 def sampler_case(name, n, t, r, seed, batch_size, ratio, np_seed):
     """Corpus.get_iteration_triples_batch (create_batch.py:262-351), the reference's own method, np.random seeded."""
     triples = make_triples(n, t, r, seed)
@@ -286,6 +306,7 @@ if __name__ == "__main__":
     loss_case("loss_small", 40, 5, 12, 30, 2, 0.5, 40)
     loss_case("loss_refdims_hub", 300, 11, 200, 700, 2, 5.0, 41, hub_share=0.9)     # entity 3 heads ~630 positives: hub segment
     loss_case("loss_ratio3_oddwidth", 50, 4, 7, 25, 3, 1.0, 42)
+    load_data_case("load_data_small", 30, 100, 5, 70)
     sampler_case("sampler_a", 60, 400, 6, 60, 20, 2, 123)
     sampler_case("sampler_dense_r1", 12, 120, 1, 61, 12, 2, 124)      # one relation: relation corruption exhausts (348-350)
     sampler_case("sampler_ratio3", 40, 200, 4, 62, 15, 3, 125)        # odd ratio: untouched +1 copies in the middle

@@ -114,3 +114,18 @@ def test_edge_oracle_toy_kg():
     assert idx == [[1, 1, 2, 3, 0, 3, 4], [0, 0, 0, 1, 1, 2, 3]]
     assert val == [5, 6, 7, 8, 2, 9, 1]
     assert OE.batch_nhop(graph, [0, 1, 2, 3]) == [[0, 5, 8, 3], [1, 8, 1, 4], [1, 2, 7, 2], [2, 9, 1, 4]]
+
+
+# ---- preprocess.load_data: triples -> adjacency (rows = tail, cols = head), all flag combinations -------------------
+@pytest.mark.parametrize("directed", [True, False])
+@pytest.mark.parametrize("unweighted", [False, True])
+def test_triples_to_adj_matches_reference_load_data(directed, unweighted):
+    import numpy as np
+    from oracle import edges as OE
+    from recon_b200 import triples_to_adj
+    g = load_golden("load_data_small")
+    want = g[f"adj.directed{int(directed)}.unweighted{int(unweighted)}"]
+    rows, cols, data = OE.triples_to_adj(g["triples"].tolist(), unweighted, directed)
+    assert np.array_equal(np.asarray([rows, cols, data]), want)
+    edge, val = triples_to_adj(torch.as_tensor(g["triples"]), unweighted, directed)       # product helper (index glue)
+    assert edge.dtype == torch.int64 and np.array_equal(edge.numpy(), want[:2]) and np.array_equal(val.numpy(), want[2])
