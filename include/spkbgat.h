@@ -300,6 +300,11 @@ int spk_sgd_step(const spk_sgd_args* args, spk_stream_t stream);
  * followed by rows*width fp32 row-major. */
 int spk_export_json(const float* host_rows, int64_t rows, int64_t width, int64_t ld, const char* path, int32_t n_threads);
 int spk_export_bin(const float* host_rows, int64_t rows, int64_t width, int64_t ld, const char* path);
+/* Reader of that JSON text (what the consumer's json.load does, train.py:103-104, without a Python object per float):
+ * spk_import_json_shape returns the number of keys and the length of the first list; spk_import_json parses
+ * {"<i>": [numbers], ...} with n_threads host threads (0 = all cores) into out[i, :width] (fp32, row stride ld). */
+int spk_import_json_shape(const char* path, int64_t* rows, int64_t* width);
+int spk_import_json(const char* path, float* out, int64_t rows, int64_t width, int64_t ld, int32_t n_threads);
 
 /* ---- N3: Corpus.get_iteration_triples_batch (GAT/create_batch.py:262-351) on the device ----
  * spk_triple_keys: key[i] = (h*R + r)*N + t of triples int64 [M,3]; pass the triples in (h, r, t) lexicographic order to

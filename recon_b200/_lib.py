@@ -177,6 +177,8 @@ SIGNATURES = {
     "spk_corrupt_triples": (_I32, [_VP, _I64, _I32, _VP, _I64, _I64, _I64, _VP, _VP, C.c_uint64, _VP, _VP, _VP]),
     "spk_export_json": (_I32, [_VP, _I64, _I64, _I64, C.c_char_p, _I32]),
     "spk_export_bin": (_I32, [_VP, _I64, _I64, _I64, C.c_char_p]),
+    "spk_import_json_shape": (_I32, [C.c_char_p, C.POINTER(_I64), C.POINTER(_I64)]),
+    "spk_import_json": (_I32, [C.c_char_p, _VP, _I64, _I64, _I64, _I32]),
 }
 
 _lib = None

@@ -172,3 +172,156 @@ int spk_export_bin(const float* host, int64_t rows, int64_t width, int64_t ld, c
 }
 
 }  // extern "C"
+
+// ---- reader of the same text (what train.py:103-104 does with json.load, minus the Python object per float) ----------
+// Works on any JSON object of the shape {"<int>": [numbers...], ...} (whitespace-insensitive): the file is mapped, cut
+// into byte ranges at key boundaries (only keys carry quotes) and parsed by all host threads with std::from_chars;
+// row "<i>" lands in out[i, :]. Values are narrowed to fp32, which is exact for text written from fp32 tables.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+namespace {
+
+struct Mapped {
+    const char* p = nullptr; size_t n = 0; int fd = -1;
+    bool open_file(const char* path) {
+        fd = ::open(path, O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) != 0) { ::close(fd); fd = -1; return false; }
+        n = (size_t)st.st_size;
+        if (n == 0) { p = ""; return true; }
+        void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m == MAP_FAILED) { ::close(fd); fd = -1; return false; }
+        p = (const char*)m;
+        return true;
+    }
+    ~Mapped() { if (p && n) munmap((void*)p, n); if (fd >= 0) ::close(fd); }
+};
+
+inline const char* skip_ws(const char* s, const char* e) {
+    while (s < e && (*s == ' ' || *s == '\n' || *s == '\t' || *s == '\r')) ++s;
+    return s;
+}
+
+// parses one number (JSON number, NaN, Infinity, -Infinity); returns nullptr on error
+inline const char* parse_number(const char* s, const char* e, float* out) {
+    if (s < e && *s == 'N') { if (e - s >= 3 && !memcmp(s, "NaN", 3)) { *out = NAN; return s + 3; } return nullptr; }
+    if (s < e && *s == 'I') { if (e - s >= 8 && !memcmp(s, "Infinity", 8)) { *out = INFINITY; return s + 8; } return nullptr; }
+    if (e - s >= 9 && !memcmp(s, "-Infinity", 9)) { *out = -INFINITY; return s + 9; }
+    double v;
+    const auto r = std::from_chars(s, e, v);
+    if (r.ec == std::errc::result_out_of_range) {           // denormal-range or huge text: let strtod decide
+        char* end = nullptr;
+        std::string tmp(s, (size_t)std::min<ptrdiff_t>(e - s, 64));
+        v = strtod(tmp.c_str(), &end);
+        if (end == tmp.c_str()) return nullptr;
+        *out = (float)v;
+        return s + (end - tmp.c_str());
+    }
+    if (r.ec != std::errc()) return nullptr;
+    *out = (float)v;
+    return r.ptr;
+}
+
+// parses rows whose key's opening quote lies in [s, stop); returns rows parsed or -1
+long parse_rows(const char* s, const char* stop, const char* e, float* out, int64_t rows, int64_t width,
+                int64_t ld) {
+    long done = 0;
+    while (true) {
+        s = (const char*)memchr(s, '"', (size_t)(e - s));
+        if (!s || s >= stop) return done;
+        ++s;
+        int64_t idx = 0;
+        const char* k0 = s;
+        while (s < e && *s >= '0' && *s <= '9') idx = idx * 10 + (*s++ - '0');
+        if (s == k0 || s >= e || *s != '"') {
+            // not "<digits>": this was the CLOSING quote of a key whose opening quote belongs to the previous range
+            // (a range may start inside a key); a closing quote is followed by [ws] ':' -- anything else is an error
+            const char* c = skip_ws(k0, e);
+            if (s == k0 && c < e && *c == ':') continue;
+            return -1;
+        }
+        if (idx >= rows) return -1;
+        s = skip_ws(s + 1, e);
+        if (s >= e || *s != ':') return -1;
+        s = skip_ws(s + 1, e);
+        if (s >= e || *s != '[') return -1;
+        s = skip_ws(s + 1, e);
+        float* row = out + idx * ld;
+        int64_t c = 0;
+        if (s < e && *s == ']') { ++s; }
+        else {
+            while (true) {
+                float v;
+                s = parse_number(s, e, &v);
+                if (!s) return -1;
+                if (c < width) row[c] = v;
+                ++c;
+                s = skip_ws(s, e);
+                if (s < e && *s == ',') { s = skip_ws(s + 1, e); continue; }
+                if (s < e && *s == ']') { ++s; break; }
+                return -1;
+            }
+        }
+        if (c != width) return -1;
+        ++done;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+/* rows = number of keys, width = length of the first row's list; 0 on success */
+int spk_import_json_shape(const char* path, int64_t* rows, int64_t* width) {
+    Mapped f;
+    if (!path || !rows || !width || !f.open_file(path)) { spk::set_error("import_json: cannot open %s", path ? path : "(null)"); return 3; }
+    const char* s = f.p; const char* e = f.p + f.n;
+    int64_t quotes = 0;
+    for (const char* q = s; (q = (const char*)memchr(q, '"', (size_t)(e - q))) != nullptr; ++q) ++quotes;
+    if (quotes % 2) { spk::set_error("import_json: unbalanced quotes in %s", path); return 5; }
+    *rows = quotes / 2;
+    *width = 0;
+    if (*rows) {
+        const char* b = (const char*)memchr(s, '[', (size_t)(e - s));
+        if (!b) { spk::set_error("import_json: no list in %s", path); return 5; }
+        b = skip_ws(b + 1, e);
+        int64_t w = 0;
+        if (b < e && *b != ']') {
+            w = 1;
+            for (; b < e && *b != ']'; ++b) if (*b == ',') ++w;
+        }
+        *width = w;
+    }
+    return 0;
+}
+
+int spk_import_json(const char* path, float* out, int64_t rows, int64_t width, int64_t ld, int32_t n_threads) {
+    Mapped f;
+    if (!path || !f.open_file(path)) { spk::set_error("import_json: cannot open %s", path ? path : "(null)"); return 3; }
+    if (rows == 0) return 0;
+    if (!out || ld < width) { spk::set_error("import_json: bad output buffer"); return 2; }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 256));
+    if (f.n < (size_t)(1 << 20)) nt = 1;
+    const char* b = f.p; const char* e = f.p + f.n;
+    std::vector<long> res((size_t)nt, 0);
+    std::vector<std::thread> th;
+    const size_t chunk = (f.n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const char* s = b + std::min(f.n, (size_t)t * chunk);
+        const char* stop = b + std::min(f.n, (size_t)(t + 1) * chunk);
+        if (nt == 1) res[0] = parse_rows(s, stop, e, out, rows, width, ld);
+        else th.emplace_back([&, t, s, stop]() { res[(size_t)t] = parse_rows(s, stop, e, out, rows, width, ld); });
+    }
+    for (auto& x : th) x.join();
+    long total = 0;
+    for (long r : res) { if (r < 0) { spk::set_error("import_json: %s is not an {\"i\": [numbers]} table of width %lld", path, (long long)width); return 5; } total += r; }
+    if (total != rows) { spk::set_error("import_json: parsed %ld of %lld rows of %s", total, (long long)rows, path); return 5; }
+    return 0;
+}
+
+}  // extern "C"

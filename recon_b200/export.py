@@ -9,6 +9,7 @@
   * `save_model(model, name, epoch, folder_name)` GAT/utils.py:26-31 — `trained_{epoch}.pth` state_dict.
   * `save_entity_relation_final_embeddings(model, output_folder)`  GAT/main.py:909-919.
 """
+import ctypes as C
 import json
 import os
 
@@ -52,11 +53,27 @@ def save_embed_binary(embeddings, save_path):
                "export_bin")
 
 
+def load_embed_array(path, n_threads=0):
+    """The [rows, width] fp32 table stored in a `save_embed` JSON file (or any `{"<i>": [numbers]}` JSON), parsed by
+    libspkbgat with all host threads instead of `json.load` building one Python float per number."""
+    lib = _lib.load()
+    rows, width = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.spk_import_json_shape(os.fsencode(path), C.byref(rows), C.byref(width)), "import_json_shape")
+    out = np.empty((rows.value, width.value), dtype=np.float32)
+    _lib.check(lib.spk_import_json(os.fsencode(path), out.ctypes.data if out.size else None, rows.value, width.value,
+                                   max(width.value, 1), int(n_threads)), "import_json")
+    return out
+
+
 class EmbeddingTable:
-    """Read-only view of a side-car file that indexes like the reference's loaded JSON: keys are the row ids as
-    `str` (ints accepted too), values the rows; `.array` is the [rows, width] fp32 memmap."""
+    """Read-only table that indexes like the reference's loaded JSON: keys are the row ids as `str` (ints accepted
+    too), values the rows as lists of Python floats; `.array` is the [rows, width] fp32 array (a memmap of the side-car
+    when built from a path, or any array handed in, e.g. `EmbeddingTable(load_embed_array(json_path))`)."""
 
     def __init__(self, path):
+        if isinstance(path, np.ndarray):
+            self.array = path
+            return
         with open(path, "rb") as f:
             hdr = f.read(64)
         if len(hdr) != 64 or hdr[:8] != BIN_MAGIC:
@@ -89,13 +106,15 @@ class EmbeddingTable:
         return ((str(i), self[i]) for i in range(len(self)))
 
 
-def load_embed(path):
-    """`path` may be the JSON written by `save_embed` (returns the dict `json.load` gives the reference consumer) or a
-    side-car `.bin` (returns an `EmbeddingTable`)."""
+def load_embed(path, as_table=False):
+    """`path` may be the JSON written by `save_embed` (returns the dict `json.load` gives the reference consumer, or with
+    `as_table=True` an `EmbeddingTable` filled by the native parser) or a side-car `.bin` (returns an `EmbeddingTable`)."""
     with open(path, "rb") as f:
         head = f.read(8)
     if head == BIN_MAGIC:
         return EmbeddingTable(path)
+    if as_table:
+        return EmbeddingTable(load_embed_array(path))
     with open(path, "r") as f:
         return json.load(f)
 

@@ -106,3 +106,54 @@ def test_save_model_and_final_embeddings(tmp_path):
     assert len(ent) == 8 and len(ent["0"]) == 8
     assert np.array_equal(load_embed(folder + "final_relation_embeddings.json.bin").array,
                           m.final_relation_embeddings.detach().numpy())
+
+
+# ---- native reader of the JSON text ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_load_embed_array_reads_reference_files(name):
+    from recon_b200.export import load_embed_array
+    want = np.load(os.path.join(GOLDEN, name + ".npy"))
+    got = load_embed_array(os.path.join(GOLDEN, name + ".json"))           # files written by the reference's own save_embed
+    assert got.dtype == np.float32 and got.shape == want.shape
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(np.signbit(got), np.signbit(want))               # -0.0 survives
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5, 0])
+def test_load_embed_array_round_trip_multithreaded(threads, tmp_path):
+    """3.5 MB of text: several byte ranges, cuts falling inside keys and numbers; random bit patterns incl. denormals."""
+    from recon_b200.export import save_embed, load_embed_array, load_embed
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2 ** 32, size=(20011, 7), dtype=np.uint64).astype(np.uint32)
+    t = bits.view(np.float32).copy()
+    p = str(tmp_path / "t.json")
+    save_embed(torch.as_tensor(t), p)
+    assert os.path.getsize(p) > (1 << 20)
+    got = load_embed_array(p, n_threads=threads)
+    finite = np.isfinite(t)
+    assert np.array_equal(got[finite].view(np.uint32), t[finite].view(np.uint32))      # bit-exact incl. denormals, -0.0
+    assert np.array_equal(np.isnan(got), np.isnan(t)) and np.array_equal(got[np.isinf(t)], t[np.isinf(t)])
+    table = load_embed(p, as_table=True)
+    ref = json.load(open(p))
+    for key in ("0", "9", "20010"):
+        a, b = table[key], ref[key]
+        assert len(a) == len(b) and all((x == y) or (x != x and y != y) for x, y in zip(a, b))
+
+
+def test_load_embed_array_other_json_layouts_and_errors(tmp_path):
+    from recon_b200.export import load_embed_array
+    data = {str(i): [float(i) + 0.25, -1e-3 * i, 3e10] for i in range(50)}
+    p = tmp_path / "compact.json"
+    p.write_text(json.dumps(data))                                           # no indentation at all
+    got = load_embed_array(str(p))
+    assert np.array_equal(got, np.asarray([data[str(i)] for i in range(50)], dtype=np.float32))
+    (tmp_path / "empty.json").write_text("{}")
+    assert load_embed_array(str(tmp_path / "empty.json")).shape == (0, 0)
+    (tmp_path / "ragged.json").write_text('{"0": [1.0, 2.0], "1": [3.0]}')
+    with pytest.raises(RuntimeError):
+        load_embed_array(str(tmp_path / "ragged.json"))
+    (tmp_path / "bad.json").write_text('{"0": [1.0, oops]}')
+    with pytest.raises(RuntimeError):
+        load_embed_array(str(tmp_path / "bad.json"))
+    with pytest.raises(RuntimeError):
+        load_embed_array(str(tmp_path / "missing.json"))
