@@ -90,29 +90,189 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def cpu_reference_arm(steps, warmup, threads=None):
-    """The reference's CPU algorithm (oracle port, COO sparse.sum path) on the C1 sample."""
-    from oracle import ref_torch as O
+def cpu_reference_arm(steps, warmup, threads=None, one_thread=True):
+    """The reference's own CPU implementation on the C1 sample: the UNMODIFIED /root/reference/GAT/{layers,models}.py
+    (copied by build() into the git-ignored oracle/_ref/, module globals CUDA pinned to False: SURVEY.md 8c/8d) through
+    its public module call; falls back to the oracle port (kind "port") only when oracle/_ref was never installed."""
+    from oracle import ref_loader
     from recon_b200.synth import make_kg
-    torch.set_num_threads(threads or os.cpu_count())
     n, e1, e2, r, alpha, _ = WORKLOADS["c1"]
     edge, etype, nhop = make_kg(n, e1, r, alpha, e2, 0)
-    p = O.init_params(n, r, F_IN, D_OUT, HEADS, seed=0)
     g = torch.Generator().manual_seed(1)
     ge, gr = torch.randn(n, D_OUT * HEADS, generator=g), torch.randn(r, D_OUT * HEADS, generator=g)
     be = torch.arange(n)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.fwd_bwd(p, be, (edge, etype), nhop, ALPHA, ge, gr)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    times.sort()
-    med = times[len(times) // 2]
-    return {"value": (e1 + e2) / med, "unit": "edges/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"C1 shape N={n} E={e1} R={r} Zipf {alpha} (largest the reference algorithm holds: it "
-                      f"materialises [2F+Rd,E]); median of {steps} fwd+bwd after {warmup} warm-ups",
-            "ms_per_step": med * 1e3}
+    ref = ref_loader.load()
+    if ref is not None:
+        kind = "reference"
+        g0 = torch.Generator().manual_seed(0)
+        ent, rel = torch.randn(n, F_IN, generator=g0), torch.randn(r, F_IN, generator=g0)
+        torch.manual_seed(0)
+        model = ref[1].SpKBGATModified(ent, rel, [D_OUT, 2 * D_OUT], [D_OUT, 2 * D_OUT], 0.0, ALPHA, [HEADS, HEADS], None)
+
+        def step():
+            model.zero_grad()
+            out_e, out_r, _ = model(None, be, (edge, etype), nhop)
+            ((out_e * ge).sum() + (out_r * gr).sum()).backward()
+    else:
+        kind = "port"
+        from oracle import ref_torch as O
+        p = O.init_params(n, r, F_IN, D_OUT, HEADS, seed=0)
+
+        def step():
+            O.fwd_bwd(p, be, (edge, etype), nhop, ALPHA, ge, gr)
+
+    def timed(nthreads, k, w):
+        torch.set_num_threads(nthreads)
+        ts = []
+        for i in range(w + k):
+            t0 = time.perf_counter()
+            step()
+            if i >= w:
+                ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cores = threads or os.cpu_count()
+        med = timed(cores, steps, warmup)
+        med1 = timed(1, 2, 1) if one_thread else None
+        torch.set_num_threads(cores)
+    out = {"value": (e1 + e2) / med, "unit": "edges/s", "cores": cores, "kind": kind,
+           "sample": f"C1 shape N={n} E={e1} R={r} Zipf {alpha} (largest the reference algorithm holds: it "
+                     f"materialises [2F+Rd,E]); median of {steps} fwd+bwd after {warmup} warm-ups, fp32, dropout off",
+           "ms_per_step": med * 1e3}
+    if med1 is not None:
+        out["one_thread"] = {"value": (e1 + e2) / med1, "unit": "edges/s", "cores": 1, "ms_per_step": med1 * 1e3}
+    return out
+
+
+def add_workload(name):
+    """c2xK: K x the C2 shape (weak-scaling family); c4h: half of C4 in both N and E (the largest power-of-two fraction
+    of the 400M-edge scale-out shape whose single-GPU step fits 180 GB: C4 itself needs ~220 GB on one GPU)."""
+    if name in WORKLOADS:
+        return
+    if name.startswith("c2x"):
+        k = int(name[3:])
+        n0, e0, _, r0, a0, h0 = WORKLOADS["c2"]
+        WORKLOADS[name] = (n0 * k, e0 * k, 0, r0, a0, h0)
+    elif name == "c4h":
+        n0, e0, _, r0, a0, h0 = WORKLOADS["c4"]
+        WORKLOADS[name] = (n0 // 2, e0 // 2, 0, r0, a0, h0)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+
+
+def describe(workload):
+    n_, e1_, e2_, r_, a_, h_ = WORKLOADS[workload]
+    return (f"{workload}: N={n_} E1={e1_} E2={e2_} R={r_} in={F_IN} entity_out=[{D_OUT},{2 * D_OUT}] "
+            f"heads=[{HEADS},{HEADS}] rows: {int(100 * h_)}% Pareto(alpha={a_}) hubs + uniform")
+
+
+def run_config(workload, world, rank, dev, steps, warmup, want_prof=False, want_e2e=False, clocks=False):
+    """Builds the runner for `workload`, runs `warmup` untimed + `steps` timed steps (CUDA events, barrier + synchronize on
+    both sides, max over ranks). Returns a dict; the runner is released before returning."""
+    import torch.distributed as dist
+    from recon_b200 import _lib, profiler
+    add_workload(workload)
+    n, r, edge, etype, nhop = make_inputs(workload, device=dev if (world > 1 or WORKLOADS[workload][1] > 50_000_000) else "cpu")
+    e_total = edge.shape[1] + nhop.shape[0]
+    if world > 1:
+        from recon_b200.dist import PartitionedKBGAT
+        runner = PartitionedKBGAT(n, r, edge, etype, nhop, F_IN, D_OUT, HEADS, ALPHA, dev)
+    else:
+        runner = SingleGPU(n, r, edge, etype, nhop, dev)
+    del edge, etype, nhop
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        runner.step()
+    barrier()
+    sampler = ClockSampler(dev.index or 0) if (clocks and rank == 0) else None
+    if sampler:
+        sampler.start()
+    torch.cuda.reset_peak_memory_stats()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        runner.step()
+    ev1.record()
+    barrier()
+    res = {"workload": workload, "e_total": e_total, "launches": _lib.launch_count() - l0,
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}
+    ms = ev0.elapsed_time(ev1) / steps
+    res["clocks"] = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lo = torch.tensor([runner.n_edges_local], device=dev, dtype=torch.float64)
+        hi = lo.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        res["edges_per_rank"] = {"min": int(lo.item()), "max": int(hi.item())}
+    res["ms"] = ms
+    if want_prof:                     # per-call timing pass (CUDA events around every C-ABI call on the launching stream)
+        prof_steps = max(2, min(steps, 5))
+        profiler.enable()
+        for _ in range(prof_steps):
+            runner.step()
+        res["prof"], res["prof_steps"] = profiler.disable(), prof_steps
+        if world == 1:
+            res["graph_build_ms"] = runner.graph_build_ms()
+    if want_e2e and world == 1:
+        res["e2e"] = runner.e2e(max(2, min(steps, 5)))
+        res["e2e_pipelined"] = runner.e2e_pipelined(max(2, min(steps, 5)))
+    elif want_e2e:
+        sec, h2d = runner.e2e(max(2, min(steps, 3)))
+        t = torch.tensor([sec, float(h2d)], device=dev, dtype=torch.float64)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        res["e2e"] = {"value": e_total / float(tmax[0]), "unit": "edges/s", "h2d_bytes_per_step": int(tsum[1]),
+                      "d2h_bytes_per_step": 4 * world, "ms_per_step": float(tmax[0]) * 1e3,
+                      "includes": "per rank: pinned H2D of its int64 edge list, device CSR/CSC/relation build, fwd+bwd "
+                                  "with the exchanges, loss D2H; max over ranks"}
+    if world == 1 and want_prof:
+        res["runner_roofline"] = runner.roofline
+        res["roofline_args"] = (res["prof"],)
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        res["roofline"] = runner.roofline(res["prof"], hbm_peak, peak_src)
+        res["hbm_peak"], res["peak_src"] = hbm_peak, peak_src
+        del res["runner_roofline"], res["roofline_args"]
+    del runner
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def config_of(workload, world):
+    """`config` of the JSON line; the reference arm prints the same object (it runs a bounded sample of this workload)."""
+    return {"workload": describe(workload),
+            "l2": "gather tables (P2 1.7 GB/layer) exceed the 126 MB L2; no flush needed",
+            "parallelism": f"row-partition x{world}" if world > 1 else "single GPU"}
+
+
+def secondary(res, world):
+    """Compact record of a secondary measurement (strong-scaling shapes) for the JSON line."""
+    n_, e1_, e2_, *_ = WORKLOADS[res["workload"]]
+    balg = b_alg_bytes(n_, e1_, e2_)
+    out = {"workload": describe(res["workload"]), "n_gpus": world, "ms_per_step": res["ms"],
+           "value": res["e_total"] / (res["ms"] * 1e-3), "unit": "edges/s", "scaling": "strong",
+           "frac_of_8TBs_per_gpu": balg / (res["ms"] * 1e-3) / 8e12 / world, "peak_mem_gb": res["peak_mem_gb"]}
+    if "edges_per_rank" in res:
+        out["edges_per_rank"] = res["edges_per_rank"]
+    return out
 
 
 def main():
@@ -124,137 +284,116 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the secondary strong-scaling shapes (c4h, c4)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--sub", action="store_true", help="(internal) secondary measurement in a child process")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    # default: the C2 shape per GPU (weak scaling): N GPUs run a graph with N x 2M entities / N x 20M edges, row-partitioned
-    # with the NCCL exchanges of SURVEY.md 8e. `--workload c4` runs the fixed 400M-edge shape (needs >= 4 GPUs of 180 GB).
-    workload = args.workload or ("c2" if world == 1 else f"c2x{world}")
-    if workload.startswith("c2x"):
-        k = int(workload[3:])
-        n0, e0, _, r0, a0, h0 = WORKLOADS["c2"]
-        WORKLOADS[workload] = (n0 * k, e0 * k, 0, r0, a0, h0)
+    # Primary line: the C2 shape per GPU (BASELINE configs[1] at N=1; N GPUs run N x 2M entities / N x 20M edges, row-
+    # partitioned: weak scaling, so the driver's per-N efficiency is well defined). Secondary keys carry BASELINE
+    # configs[3] (C4, 400M edges; N >= 4) and its half c4h (fits one GPU) as STRONG-scaling measurements at every N.
+    default_mode = args.workload is None
+    workload = args.workload or ("c2" if max(world, args.gpus) == 1 else f"c2x{max(world, args.gpus)}")
+    add_workload(workload)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        n, e1, e2, r, alpha, hub = WORKLOADS[workload]
         base = cpu_reference_arm(max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
         line = {"impl": "reference", "metric": "SpKBGAT fwd+bwd edges/sec", "value": base["value"], "unit": "edges/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
-                "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{workload}: N={n} E={e1 + e2} R={r} (reference arm runs the bounded C1 sample)"},
-                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "config": config_of(workload, args.gpus),
+                "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "one_thread") if k in base},
                 "e2e": {"value": base["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
-    from recon_b200 import SpKBGATModified, _lib
-    from recon_b200 import profiler
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    # multi-GPU: every rank generates the same graph on its own device (same seed, same device type)
-    n, r, edge, etype, nhop = make_inputs(workload, device=dev if world > 1 else "cpu")
-    e_total = edge.shape[1] + nhop.shape[0]
 
-    if world > 1:
-        from recon_b200.dist import PartitionedKBGAT
-        runner = PartitionedKBGAT(n, r, edge, etype, nhop, F_IN, D_OUT, HEADS, ALPHA, dev)
-        del edge, etype, nhop
-        torch.cuda.empty_cache()
-    else:
-        runner = SingleGPU(n, r, edge, etype, nhop, dev)
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        runner.step()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = _lib.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        runner.step()
-    ev1.record()
-    barrier()
-    launches = _lib.launch_count() - l0
-    ms = ev0.elapsed_time(ev1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-
-    # per-kernel timing pass (CUDA events around every C-ABI call on the launching stream)
-    prof_steps = max(2, min(args.steps, 5))
-    profiler.enable()
-    for _ in range(prof_steps):
-        runner.step()
-    prof = profiler.disable()
-
-    e2e = None
-    e2e_pipe = None
-    if not args.no_e2e and world == 1:
-        e2e = runner.e2e(max(2, min(args.steps, 5)))
-        e2e_pipe = runner.e2e_pipelined(max(2, min(args.steps, 5)))
-    elif not args.no_e2e:
-        import torch.distributed as dist
-        sec, h2d = runner.e2e(max(2, min(args.steps, 3)))
-        t = torch.tensor([sec, float(h2d)], device=dev, dtype=torch.float64)
-        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        e2e = {"value": e_total / float(tmax[0]), "unit": "edges/s", "h2d_bytes_per_step": int(tsum[1]),
-               "d2h_bytes_per_step": 4 * world, "ms_per_step": float(tmax[0]) * 1e3,
-               "includes": "per rank: pinned H2D of its int64 edge list, device CSR/CSC/relation build, fwd+bwd with "
-                           "NCCL exchanges, loss D2H; max over ranks"}
-
-    if rank != 0:
+    if args.sub:                       # child of a 1-GPU run: one secondary shape, compact line
+        res = run_config(workload, world, rank, dev, args.steps, args.warmup)
+        print("SUB " + json.dumps(secondary(res, world)))
         return
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        peaks = json.load(open(pk))
-    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    n_, e1_, e2_, *_ = WORKLOADS[workload]
-    roof = runner.roofline(prof, hbm_peak, peak_src) if world == 1 else None
-    value = e_total / (ms * 1e-3)
-    balg = b_alg_bytes(n_, e1_, e2_)
-    line = {"metric": "SpKBGAT fwd+bwd edges/sec", "value": value, "unit": "edges/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak" if (world == 1 or workload.startswith("c2x")) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{workload}: N={n_} E1={e1_} E2={e2_} R={WORKLOADS[workload][3]} in={F_IN} "
-                                   f"entity_out=[{D_OUT},{2 * D_OUT}] heads=[{HEADS},{HEADS}] rows: "
-                                   f"{int(100 * WORKLOADS[workload][5])}% Pareto(alpha={WORKLOADS[workload][4]}) hubs + uniform",
-                       "l2": "gather tables (P2 1.7 GB/layer) exceed the 126 MB L2; no flush needed",
-                       "parallelism": f"row-partition x{world}" if world > 1 else "single GPU"},
-            "clocks": clocks, "gpu_launches": launches,
-            "step_roofline": {"b_alg_bytes": balg, "achieved_gbs": balg / (ms * 1e-3) / 1e9,
-                              "frac_of_8TBs": balg / (ms * 1e-3) / 8e12,
-                              "frac_of_measured": balg / (ms * 1e-3) / (hbm_peak * 1e9), "peak_source": peak_src},
-            "kernels_ms_per_step": {k: round(v[0] / prof_steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
-    if roof:
-        line["roofline"] = roof
-    if e2e:
-        line["e2e"] = e2e
-    if e2e_pipe:
-        line["e2e_pipelined"] = e2e_pipe
-    if not args.no_cpu_baseline and world == 1:
+
+    res = run_config(workload, world, rank, dev, args.steps, args.warmup, want_prof=True, want_e2e=not args.no_e2e,
+                     clocks=True)
+    ms, e_total = res["ms"], res["e_total"]
+    line = None
+    if rank == 0:
+        hbm_peak, peak_src = res.get("hbm_peak"), res.get("peak_src")
+        if hbm_peak is None:
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            peaks = json.load(open(pk)) if os.path.exists(pk) else {}
+            hbm_peak, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        n_, e1_, e2_, *_ = WORKLOADS[workload]
+        balg = b_alg_bytes(n_, e1_, e2_)
+        prof, prof_steps = res["prof"], res["prof_steps"]
+        line = {"metric": "SpKBGAT fwd+bwd edges/sec", "value": e_total / (ms * 1e-3), "unit": "edges/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak" if (world == 1 or workload.startswith("c2x")) else "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": config_of(workload, world),
+                "clocks": res["clocks"], "gpu_launches": res["launches"], "peak_mem_gb": res["peak_mem_gb"],
+                "step_roofline": {"b_alg_bytes": balg, "achieved_gbs": balg / (ms * 1e-3) / 1e9 / world,
+                                  "frac_of_8TBs": balg / (ms * 1e-3) / 8e12 / world,
+                                  "frac_of_measured": balg / (ms * 1e-3) / (hbm_peak * 1e9) / world,
+                                  "peak_source": peak_src, "per": "GPU"},
+                "kernels_ms_per_step": {k: round(v[0] / prof_steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+        for k in ("roofline", "e2e", "e2e_pipelined", "graph_build_ms", "edges_per_rank"):
+            if res.get(k):
+                line[k] = res[k]
+
+    # ---- secondary sections; a watchdog prints what exists if one of them stalls (e.g. a rank out of memory inside a
+    # collective), so the primary measurement is never lost ----
+    import threading
+
+    def bail():
+        if rank == 0 and line is not None:
+            line.setdefault("notes", []).append("secondary section timed out; primary line printed by the watchdog")
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+
+    dog = threading.Timer(420.0, bail)
+    dog.daemon = True
+    dog.start()
+    if default_mode and not args.no_strong:
+        shapes = ["c4h"] + (["c4"] if world >= 4 else [])
+        for w in shapes:
+            try:
+                if world == 1:        # child process: an out-of-memory C4 attempt cannot take the primary line with it
+                    if rank == 0:
+                        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", w, "--steps", "3",
+                                            "--warmup", "2", "--sub"], capture_output=True, text=True, timeout=300)
+                        sub = [l for l in p.stdout.splitlines() if l.startswith("SUB ")]
+                        line[w] = json.loads(sub[-1][4:]) if sub else {"error": (p.stderr or p.stdout)[-300:]}
+                else:
+                    r2 = run_config(w, world, rank, dev, 3, 2)
+                    if rank == 0:
+                        line[w] = secondary(r2, world)
+            except Exception as exc:                 # noqa: BLE001
+                if rank == 0:
+                    line[w] = {"error": repr(exc)[:300]}
+                if world > 1:
+                    raise
+    if world > 1 and not args.no_parity:
+        from recon_b200.dist import parity_check
+        par = parity_check(dev)
+        if rank == 0:
+            line["parity"] = par
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
         base = cpu_reference_arm(3, 1)
-        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+        line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "one_thread") if k in base}
+    dog.cancel()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -285,6 +424,21 @@ class SingleGPU:
         loss = torch.dot(out_e.reshape(-1), self.g_ent.reshape(-1)) + torch.dot(out_r.reshape(-1), self.g_rel.reshape(-1))
         loss.backward()
         return loss
+
+    def graph_build_ms(self, reps=3):
+        """CSR + CSC + relation layouts from the device-resident int64 edge tensors (per graph, amortised over epochs;
+        SURVEY.md 8d asks for it separately): CUDA events, mean of `reps` builds after one warm-up."""
+        from recon_b200 import KGraph
+        nh = self.nhop if self.nhop.numel() else None
+        KGraph(self.edge, self.etype, nh, self.n, self.r, device=self.dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(reps):
+            KGraph(self.edge, self.etype, nh, self.n, self.r, device=self.dev)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
 
     def e2e(self, steps):
         from recon_b200 import KGraph

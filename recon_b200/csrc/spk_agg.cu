@@ -417,21 +417,15 @@ int launch_agg_fwd_t(const AggFwdArgs& a, cudaStream_t s) {
     constexpr int G = 4, NG = HAS2 ? 3 : 4;
     const uint32_t rbx = (uint32_t)(a.g.Fx4 + 1) * 16u, rbr = (uint32_t)(a.g.Fr4 + 1) * 16u;
     const size_t smem = (size_t)AGS_WARPS * ags_warp_bytes_c<HAS2, G, NG>(rbx, rbr);
-    static size_t set_rows = 0, set_tasks = 0;
+    static SmemLimit lim_rows, lim_tasks;
     if (a.n_rows > 0) {
-        if (set_rows < smem) {
-            cudaFuncSetAttribute(agg_fwd_stream_kernel<HT, HAS2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_rows = smem;
-        }
+        lim_rows.ensure(agg_fwd_stream_kernel<HT, HAS2, false>, smem);
         const unsigned grid = (unsigned)((a.n_rows + 32L * AGS_WARPS - 1) / (32L * AGS_WARPS));
         agg_fwd_stream_kernel<HT, HAS2, false><<<grid, AGS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("agg_fwd_stream_rows")) return rc;
     }
     if (a.hub.n_tasks > 0) {
-        if (set_tasks < smem) {
-            cudaFuncSetAttribute(agg_fwd_stream_kernel<HT, HAS2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_tasks = smem;
-        }
+        lim_tasks.ensure(agg_fwd_stream_kernel<HT, HAS2, true>, smem);
         const unsigned grid = (a.hub.n_tasks + AGS_WARPS - 1) / AGS_WARPS;
         agg_fwd_stream_kernel<HT, HAS2, true><<<grid, AGS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("agg_fwd_stream_tasks")) return rc;
@@ -738,23 +732,17 @@ int launch_agg_bwd_t(const AggBwdArgs& a, cudaStream_t s) {
     constexpr int G = 8, NG = 2;
     const uint32_t rbx = (uint32_t)(a.g.Fx4 + 1) * 16u, rbr = (uint32_t)(a.g.Fr4 + 1) * 16u;
     const size_t smem = (size_t)AGS_WARPS * ags_warp_bytes_c<HAS2, G, NG>(rbx, rbr);
-    static size_t set_rows = 0, set_tasks = 0;
+    static SmemLimit lim_rows, lim_tasks;
     if (a.n_rows > 0) {
         agg_bwd_ctx_kernel<<<(a.n_rows + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("agg_bwd_ctx")) return rc;
-        if (set_rows < smem) {
-            cudaFuncSetAttribute(agg_bwd_stream_kernel<HT, HAS2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_rows = smem;
-        }
+        lim_rows.ensure(agg_bwd_stream_kernel<HT, HAS2, false>, smem);
         const unsigned grid = (unsigned)((a.n_rows + 32L * AGS_WARPS - 1) / (32L * AGS_WARPS));
         agg_bwd_stream_kernel<HT, HAS2, false><<<grid, AGS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("agg_bwd_stream_rows")) return rc;
     }
     if (a.hub.n_tasks > 0) {
-        if (set_tasks < smem) {
-            cudaFuncSetAttribute(agg_bwd_stream_kernel<HT, HAS2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_tasks = smem;
-        }
+        lim_tasks.ensure(agg_bwd_stream_kernel<HT, HAS2, true>, smem);
         const unsigned grid = (a.hub.n_tasks + AGS_WARPS - 1) / AGS_WARPS;
         agg_bwd_stream_kernel<HT, HAS2, true><<<grid, AGS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("agg_bwd_stream_tasks")) return rc;

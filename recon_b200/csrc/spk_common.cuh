@@ -14,6 +14,21 @@ namespace spk {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // returns 0 or error code after a kernel launch
 
+// Raises a kernel's dynamic shared-memory limit. The attribute is per device, so the cache is keyed by the current
+// device id; entries only grow and the driver call is idempotent, so concurrent callers at worst repeat it.
+struct SmemLimit {
+    size_t set[64] = {};
+    template <class K>
+    cudaError_t ensure(K kernel, size_t bytes) {
+        int dev = 0;
+        const bool keyed = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64;
+        if (keyed && set[dev] >= bytes) return cudaSuccess;
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess && keyed) set[dev] = bytes;
+        return e;
+    }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -352,21 +352,15 @@ size_t bwd_stream_smem(const LayerGeom& g) {
 template <int NCH, int HT, bool HAS2>
 int launch_t(const EdgeBwdRowsArgs& a, cudaStream_t s, int (*finalize)(const EdgeBwdRowsArgs&, cudaStream_t)) {
     const size_t smem = bwd_stream_smem<NCH, HAS2>(a.g);
-    static size_t set_rows = 0, set_tasks = 0;
+    static SmemLimit lim_rows, lim_tasks;
     if (a.n_rows > 0) {
-        if (set_rows < smem) {
-            cudaFuncSetAttribute(edge_bwd_rows_stream_kernel<NCH, HT, HAS2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_rows = smem;
-        }
+        lim_rows.ensure(edge_bwd_rows_stream_kernel<NCH, HT, HAS2, false>, smem);
         const unsigned grid = (unsigned)((a.n_rows + 32L * BS_WARPS - 1) / (32L * BS_WARPS));
         edge_bwd_rows_stream_kernel<NCH, HT, HAS2, false><<<grid, BS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("edge_bwd_rows_stream")) return rc;
     }
     if (a.hub.n_tasks > 0) {
-        if (set_tasks < smem) {
-            cudaFuncSetAttribute(edge_bwd_rows_stream_kernel<NCH, HT, HAS2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_tasks = smem;
-        }
+        lim_tasks.ensure(edge_bwd_rows_stream_kernel<NCH, HT, HAS2, true>, smem);
         const unsigned grid = (a.hub.n_tasks + BS_WARPS - 1) / BS_WARPS;
         edge_bwd_rows_stream_kernel<NCH, HT, HAS2, true><<<grid, BS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("edge_bwd_rows_stream_tasks")) return rc;

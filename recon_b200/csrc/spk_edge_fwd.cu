@@ -506,21 +506,15 @@ static int fwd_variant() {
 template <int NCH, int HT, bool HAS2, int NGV, int MINB>
 static int launch_fwd_stream_v(const EdgeFwdArgs& a, cudaStream_t s) {
     const size_t smem = stream_smem_bytes<NCH, HAS2, NGV>(a.g);
-    static size_t set_rows = 0, set_tasks = 0;
+    static SmemLimit lim_rows, lim_tasks;
     if (a.n_rows > 0) {
-        if (set_rows < smem) {
-            cudaFuncSetAttribute(edge_fwd_stream_kernel<NCH, HT, HAS2, false, NGV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_rows = smem;
-        }
+        lim_rows.ensure(edge_fwd_stream_kernel<NCH, HT, HAS2, false, NGV, MINB>, smem);
         const unsigned grid = (unsigned)((a.n_rows + 32L * STREAM_WARPS - 1) / (32L * STREAM_WARPS));
         edge_fwd_stream_kernel<NCH, HT, HAS2, false, NGV, MINB><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("edge_fwd_stream_rows")) return rc;
     }
     if (a.hub.n_tasks > 0) {
-        if (set_tasks < smem) {
-            cudaFuncSetAttribute(edge_fwd_stream_kernel<NCH, HT, HAS2, true, NGV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_tasks = smem;
-        }
+        lim_tasks.ensure(edge_fwd_stream_kernel<NCH, HT, HAS2, true, NGV, MINB>, smem);
         const unsigned grid = (a.hub.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS;
         edge_fwd_stream_kernel<NCH, HT, HAS2, true, NGV, MINB><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("edge_fwd_stream_tasks")) return rc;
@@ -541,21 +535,15 @@ static int launch_fwd_t(const EdgeFwdArgs& a, cudaStream_t s) {
     if (use_stream() && NCH <= 2 && !HAS2 && fwd_variant() == 1) return launch_fwd_stream_v<NCH, HT, HAS2, 2, 3>(a, s);
     if (use_stream()) {
         const size_t smem = stream_smem_bytes<NCH, HAS2>(a.g);
-        static size_t set_rows = 0, set_tasks = 0;
-        if (set_rows < smem) {
-            cudaFuncSetAttribute(edge_fwd_stream_kernel<NCH, HT, HAS2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_rows = smem;
-        }
+        static SmemLimit lim_rows, lim_tasks;
+        lim_rows.ensure(edge_fwd_stream_kernel<NCH, HT, HAS2, false>, smem);
         if (a.n_rows > 0) {
             const unsigned grid = (unsigned)((a.n_rows + 32L * STREAM_WARPS - 1) / (32L * STREAM_WARPS));
             edge_fwd_stream_kernel<NCH, HT, HAS2, false><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
             if (int rc = check_launch("edge_fwd_stream_rows")) return rc;
         }
         if (a.hub.n_tasks > 0) {
-            if (set_tasks < smem) {
-                cudaFuncSetAttribute(edge_fwd_stream_kernel<NCH, HT, HAS2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                set_tasks = smem;
-            }
+            lim_tasks.ensure(edge_fwd_stream_kernel<NCH, HT, HAS2, true>, smem);
             const unsigned grid = (a.hub.n_tasks + STREAM_WARPS - 1) / STREAM_WARPS;
             edge_fwd_stream_kernel<NCH, HT, HAS2, true><<<grid, STREAM_WARPS * 32, smem, s>>>(a);
             if (int rc = check_launch("edge_fwd_stream_tasks")) return rc;

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <vector>
 
@@ -228,7 +229,7 @@ inline const char* parse_number(const char* s, const char* e, float* out) {
 
 // parses rows whose key's opening quote lies in [s, stop); returns rows parsed or -1
 long parse_rows(const char* s, const char* stop, const char* e, float* out, int64_t rows, int64_t width,
-                int64_t ld) {
+                int64_t ld, std::atomic<uint8_t>* seen) {
     long done = 0;
     while (true) {
         s = (const char*)memchr(s, '"', (size_t)(e - s));
@@ -236,7 +237,8 @@ long parse_rows(const char* s, const char* stop, const char* e, float* out, int6
         ++s;
         int64_t idx = 0;
         const char* k0 = s;
-        while (s < e && *s >= '0' && *s <= '9') idx = idx * 10 + (*s++ - '0');
+        while (s < e && *s >= '0' && *s <= '9' && s - k0 < 19) idx = idx * 10 + (*s++ - '0');   // <= 18 digits: no overflow
+        if (s - k0 >= 19) return -1;
         if (s == k0 || s >= e || *s != '"') {
             // not "<digits>": this was the CLOSING quote of a key whose opening quote belongs to the previous range
             // (a range may start inside a key); a closing quote is followed by [ws] ':' -- anything else is an error
@@ -244,7 +246,8 @@ long parse_rows(const char* s, const char* stop, const char* e, float* out, int6
             if (s == k0 && c < e && *c == ':') continue;
             return -1;
         }
-        if (idx >= rows) return -1;
+        if (idx < 0 || idx >= rows) return -1;
+        if (seen[idx].exchange(1, std::memory_order_relaxed)) return -1;      // duplicate key: json.load would return fewer rows
         s = skip_ws(s + 1, e);
         if (s >= e || *s != ':') return -1;
         s = skip_ws(s + 1, e);
@@ -309,13 +312,15 @@ int spk_import_json(const char* path, float* out, int64_t rows, int64_t width, i
     if (f.n < (size_t)(1 << 20)) nt = 1;
     const char* b = f.p; const char* e = f.p + f.n;
     std::vector<long> res((size_t)nt, 0);
+    std::vector<std::atomic<uint8_t>> seen((size_t)rows);                      // every key exactly once (total == rows below)
+    for (auto& x : seen) x.store(0, std::memory_order_relaxed);
     std::vector<std::thread> th;
     const size_t chunk = (f.n + nt - 1) / nt;
     for (int t = 0; t < nt; ++t) {
         const char* s = b + std::min(f.n, (size_t)t * chunk);
         const char* stop = b + std::min(f.n, (size_t)(t + 1) * chunk);
-        if (nt == 1) res[0] = parse_rows(s, stop, e, out, rows, width, ld);
-        else th.emplace_back([&, t, s, stop]() { res[(size_t)t] = parse_rows(s, stop, e, out, rows, width, ld); });
+        if (nt == 1) res[0] = parse_rows(s, stop, e, out, rows, width, ld, seen.data());
+        else th.emplace_back([&, t, s, stop]() { res[(size_t)t] = parse_rows(s, stop, e, out, rows, width, ld, seen.data()); });
     }
     for (auto& x : th) x.join();
     long total = 0;

@@ -413,14 +413,11 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.n_tiles_n = n_tiles_n; p.stages = stages;
     p.accumulate = accumulate; p.act = act;
     p.c_vec = c_vec; p.c_tma = c_tma; p.raw_hi = tc_raw_hi();
-    static int smem_set = 0;
-    if (smem_set < smem) {
-        if (cudaFuncSetAttribute(gemm_nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
-            set_error("gemm_tc: cannot raise dynamic shared memory limit");
-            (void)cudaGetLastError();
-            return 3;
-        }
-        smem_set = 226 * 1024;
+    static SmemLimit lim;
+    if (lim.ensure(gemm_nn_tc_kernel, 226 * 1024) != cudaSuccess) {
+        set_error("gemm_tc: cannot raise dynamic shared memory limit");
+        (void)cudaGetLastError();
+        return 3;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -679,14 +676,11 @@ int gemm_tn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     TnParams p;
     p.part = workspace; p.M = M; p.Ka = Ka; p.Nb = Nb; p.BN = pl.BN; p.n_tiles_n = pl.n_tiles_n; p.n_tiles_k = pl.n_tiles_k;
     p.splits = pl.splits; p.m_per_split = pl.m_per_split; p.stages = pl.stages; p.raw_hi = tc_raw_hi();
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024) != cudaSuccess) {
-            set_error("gemm_tn_tc: cannot raise dynamic shared memory limit");
-            (void)cudaGetLastError();
-            return 3;
-        }
-        attr_set = true;
+    static SmemLimit lim;
+    if (lim.ensure(gemm_tn_tc_kernel, 226 * 1024) != cudaSuccess) {
+        set_error("gemm_tn_tc: cannot raise dynamic shared memory limit");
+        (void)cudaGetLastError();
+        return 3;
     }
     const unsigned grid = (unsigned)(pl.n_tiles_k * pl.n_tiles_n * pl.splits);
     gemm_tn_tc_kernel<<<grid, TN_THREADS, pl.smem, s>>>(tmX, tmG, p);

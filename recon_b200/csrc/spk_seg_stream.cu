@@ -203,21 +203,15 @@ seg_gather_stream_kernel(const SegGatherArgs a) {
 template <int NCH, int HT>
 int launch_t(const SegGatherArgs& a, cudaStream_t s) {
     const size_t smem = SS_WARPS * ((size_t)SS_SLOTS * a.ldg * 4 + 128);
-    static size_t set_rows = 0, set_tasks = 0;
+    static SmemLimit lim_rows, lim_tasks;
     if (a.n_seg > 0) {
-        if (set_rows < smem) {
-            cudaFuncSetAttribute(seg_gather_stream_kernel<NCH, HT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_rows = smem;
-        }
+        lim_rows.ensure(seg_gather_stream_kernel<NCH, HT, false>, smem);
         const unsigned grid = (unsigned)((a.n_seg + 32L * SS_WARPS - 1) / (32L * SS_WARPS));
         seg_gather_stream_kernel<NCH, HT, false><<<grid, SS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("seg_gather_stream")) return rc;
     }
     if (a.hub.n_tasks > 0) {
-        if (set_tasks < smem) {
-            cudaFuncSetAttribute(seg_gather_stream_kernel<NCH, HT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            set_tasks = smem;
-        }
+        lim_tasks.ensure(seg_gather_stream_kernel<NCH, HT, true>, smem);
         const unsigned grid = (a.hub.n_tasks + SS_WARPS - 1) / SS_WARPS;
         seg_gather_stream_kernel<NCH, HT, true><<<grid, SS_WARPS * 32, smem, s>>>(a);
         if (int rc = check_launch("seg_gather_stream_tasks")) return rc;

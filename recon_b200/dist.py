@@ -191,3 +191,54 @@ class PartitionedKBGAT:
         loss = (out_e * self.g_ent).sum() + (out_r * self.g_rel).sum()
         loss.backward()
         return out_e, out_r, loss
+
+
+def parity_check(device, group=None, n=20000, e=200000, r=64, n_nhop=0, seed=21, in_dim=50, out_dim=100, nheads=2,
+                 alpha=0.2, zipf=1.1):
+    """Multi-GPU parity against the single-GPU path of this library on one small seeded KG ("results
+    identical (<= 1e-6 rel) to the 1-GPU run"): every rank runs the row-partitioned step, rank 0 also runs the whole
+    graph on its own GPU; returns {"max_rel": worst rel-L2 over out_entity, out_relation and every gradient, ...} on
+    every rank. Used by bench.py (printed in the JSON line at N > 1) and tests/test_dist_gpu.py."""
+    from .models import SpKBGATModified
+    from .synth import make_kg
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    edge, etype, nhop = make_kg(n, e, r, alpha=zipf, n_nhop=n_nhop, seed=seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    ent = torch.randn(n, in_dim, generator=gen)
+    rel = torch.randn(r, in_dim, generator=gen)
+    torch.manual_seed(seed)
+    ref = SpKBGATModified(ent.clone(), rel.clone(), [out_dim, 2 * out_dim], [out_dim, 2 * out_dim], 0.0, alpha,
+                          [nheads, nheads], None)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    g_ent = torch.randn(n, out_dim * nheads, generator=gen)
+    g_rel = torch.randn(r, out_dim * nheads, generator=gen)
+    pk = PartitionedKBGAT(n, r, edge, etype, nhop, in_dim, out_dim, nheads, alpha, device, group=group, state_dict=sd)
+    pk.set_loss_weights(g_ent, g_rel)
+    out_e, out_r, _ = pk.step()
+    torch.cuda.synchronize()
+    lo, hi = pk.lo, pk.hi
+    gathered = {}
+    for k, t in (("out_entity", out_e.detach()), ("grad.entity_embeddings", pk.model.entity_embeddings.grad)):
+        full = torch.zeros(n, t.shape[1], device=device)
+        full[lo:hi] = t
+        dist.all_reduce(full, group=group)
+        gathered[k] = full
+    res = torch.zeros(2, dtype=torch.float64, device=device)
+    if rank == 0:
+        def rl(a, b):
+            a = a.detach().double(); b = b.detach().double()
+            return float((a - b).norm() / b.norm().clamp_min(1e-30))
+        m = ref.to(device)
+        m.load_state_dict(sd)
+        oe, orl, _ = m(None, torch.arange(n), (edge, etype), nhop)
+        ((oe * g_ent.to(device)).sum() + (orl * g_rel.to(device)).sum()).backward()
+        errs = {"out_entity": rl(gathered["out_entity"], oe), "out_relation": rl(out_r, orl),
+                "grad.entity_embeddings": rl(gathered["grad.entity_embeddings"], m.entity_embeddings.grad)}
+        refp = dict(m.named_parameters())
+        for k, prm in pk.model.named_parameters():
+            if k not in ("entity_embeddings", "final_entity_embeddings", "final_relation_embeddings") and prm.grad is not None:
+                errs["grad." + k] = rl(prm.grad, refp[k].grad)
+        res[0] = max(errs.values()); res[1] = len(errs)
+    dist.broadcast(res, 0, group=group)
+    return {"max_rel": float(res[0]), "tensors": int(res[1]), "world": world,
+            "vs": f"single-GPU path on the same KG (N={n} E={e + n_nhop} R={r}, Zipf {zipf})"}

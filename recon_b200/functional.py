@@ -578,6 +578,16 @@ class AggGroupFn(torch.autograd.Function):
 def attention_group(X, Rel, a_list, a2_list, graph, alpha, apply_elu, mask_csr, nanflag):
     """All heads of one layer (looping over groups of <=4): returns [N, sum_h D]."""
     outs = []
+    # the C ABI takes raw pointers without row counts: check here what the reference's indexing would have caught
+    # (IndexError from x[edge[..]] / relation_embed[edge_type], GAT/layers.py:129, models.py:156)
+    if X.shape[0] != graph.n_nodes:
+        raise IndexError(f"entity table has {X.shape[0]} rows but the graph was built for {graph.n_nodes} nodes")
+    if getattr(graph, "dist", None) is None and graph.n_cols > X.shape[0]:
+        raise IndexError(f"graph gathers from {graph.n_cols} nodes but the entity table has {X.shape[0]} rows")
+    if Rel.shape[0] < graph.n_rel:
+        raise IndexError(f"relation table has {Rel.shape[0]} rows but the graph uses {graph.n_rel} relations")
+    if X.device != graph.device or Rel.device != graph.device:
+        raise RuntimeError(f"tables on {X.device} / {Rel.device} but the graph layouts live on {graph.device}")
     F = X.shape[1]
     D = a_list[0].shape[0]
     Rd = a_list[0].shape[1] - 2 * F

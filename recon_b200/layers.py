@@ -23,6 +23,12 @@ class SpecialSpmmFunctionFinal(torch.autograd.Function):
         if not edge_w.is_cuda:
             raise RuntimeError("recon_b200.SpecialSpmmFunctionFinal needs CUDA tensors (no CPU fallback)")
         dev = edge_w.device
+        with torch.cuda.device(dev):
+            return SpecialSpmmFunctionFinal._forward(ctx, edge, edge_w, N, dev)
+
+    @staticmethod
+    def _forward(ctx, edge, edge_w, N, dev):
+        lib = _lib.load()
         rows64 = edge[0].to(device=dev, dtype=torch.int64).contiguous()
         if rows64.numel() and (int(rows64.min()) < 0 or int(rows64.max()) >= N):
             raise IndexError("edge row index out of range")
@@ -96,6 +102,10 @@ class SpGraphAttentionLayer(nn.Module):
         `dropout_mask`: optional [E] multipliers in the caller's edge order (extension for parity tests)."""
         if not input.is_cuda:
             raise RuntimeError("recon_b200.SpGraphAttentionLayer needs CUDA tensors (no CPU fallback)")
+        with torch.cuda.device(input.device):
+            return self._forward(input, edge, edge_embed, edge_list_nhop, edge_embed_nhop, dropout_mask)
+
+    def _forward(self, input, edge, edge_embed, edge_list_nhop, edge_embed_nhop, dropout_mask):
         dev = input.device
         n = input.shape[0]
         has2 = edge_list_nhop is not None and edge_list_nhop.numel() > 0
@@ -103,6 +113,8 @@ class SpGraphAttentionLayer(nn.Module):
             edge = torch.cat((edge.to(dev), edge_list_nhop.to(dev)), dim=1)
             edge_embed = torch.cat((edge_embed, edge_embed_nhop.to(dev)), dim=0)
         e = edge.shape[1]
+        if edge_embed.shape[0] != e:                     # torch.cat(..., dim=1) at layers.py:129 raises the same way
+            raise RuntimeError(f"edge_embed has {edge_embed.shape[0]} rows for {e} edges")
         etype = torch.arange(e, device=dev, dtype=torch.int64)
         graph = KGraph(edge.to(dev), etype, None, n, max(e, 1), device=dev)
         p = self.dropout.p

@@ -14,6 +14,15 @@ from .graph import KGraph
 from .layers import SpGraphAttentionLayer, ConvKB, check_nanflag, edge_dropout_mask  # noqa: F401
 
 
+def _fingerprint(t):
+    """A few elements of a host index tensor (no device sync for CUDA tensors: identity + version only there)."""
+    if t.is_cuda or t.numel() == 0:
+        return None
+    flat = t.reshape(-1)
+    n = flat.numel()
+    return tuple(int(flat[i]) for i in sorted({0, n // 3, n // 2, (2 * n) // 3, n - 1}))
+
+
 def _nhop_rows(edge_list_nhop, edge_type_nhop):
     """([t; s], [r1, r2]) (models.py:145-148) -> rows [s, r1, r2, t]."""
     if edge_type_nhop is None or edge_type_nhop.numel() == 0:
@@ -45,6 +54,12 @@ class SpGAT(nn.Module):
         x = entity_embeddings
         if not x.is_cuda:
             raise RuntimeError("recon_b200.SpGAT needs CUDA tensors (no CPU fallback)")
+        dev = x.device
+        with torch.cuda.device(dev):          # launch on the tensors' device, whatever the caller's current device is
+            return self._forward(x, relation_embed, edge_list, edge_type, edge_list_nhop, edge_type_nhop, graph,
+                                 dropout_masks, nanflag)
+
+    def _forward(self, x, relation_embed, edge_list, edge_type, edge_list_nhop, edge_type_nhop, graph, dropout_masks, nanflag):
         dev = x.device
         if graph is None:
             graph = KGraph(edge_list, edge_type, _nhop_rows(edge_list_nhop, edge_type_nhop), x.shape[0],
@@ -105,6 +120,7 @@ class SpKBGATModified(nn.Module):
         self.W_entities = nn.Parameter(torch.zeros(size=(self.entity_in_dim, hd)))
         nn.init.xavier_uniform_(self.W_entities.data, gain=1.414)
         self._graph_cache = {}
+        self.graph_cache = True
 
     # -- graph handling ------------------------------------------------------------------------
     def prepare_graph(self, adj, train_indices_nhop=None):
@@ -113,21 +129,29 @@ class SpKBGATModified(nn.Module):
             return adj
         edge_list, edge_type = adj[0], adj[1]
         has2 = train_indices_nhop is not None and train_indices_nhop.numel() > 0
-        key = tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device)) for t in
-                    ((edge_list, edge_type, train_indices_nhop) if has2 else (edge_list, edge_type)))
-        g = self._graph_cache.get(key)
+        dev = self.entity_embeddings.device
+        if dev.type != "cuda":
+            raise RuntimeError("recon_b200.SpKBGATModified must live on a CUDA device (no CPU fallback)")
+        tensors = (edge_list, edge_type, train_indices_nhop) if has2 else (edge_list, edge_type)
+        # identity + version + a cheap content fingerprint (first / middle / last elements, read on the host only for
+        # CPU tensors) + the model's device; writes that bypass the version counter (numpy views, .data) mostly change it.
+        # `model.graph_cache = False` disables caching altogether.
+        key = (str(dev),) + tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device), _fingerprint(t)) for t in tensors)
+        g = self._graph_cache.get(key) if self.graph_cache else None
         if g is None:
-            dev = self.entity_embeddings.device
-            if dev.type != "cuda":
-                raise RuntimeError("recon_b200.SpKBGATModified must live on a CUDA device (no CPU fallback)")
             nhop = train_indices_nhop if has2 else None
-            g = KGraph(edge_list, edge_type, nhop, self.num_nodes, self.num_relation, device=dev)
+            with torch.cuda.device(dev):
+                g = KGraph(edge_list, edge_type, nhop, self.num_nodes, self.num_relation, device=dev)
             self._graph_cache.clear()                      # keep one graph: batches change every iteration
             self._graph_cache[key] = g
             g._keepalive = (edge_list, edge_type, train_indices_nhop)   # data_ptr keys stay valid while cached
         return g
 
     def _run(self, entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks):
+        with torch.cuda.device(entity_embeddings.device):
+            return self._run_on(entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks)
+
+    def _run_on(self, entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks):
         dev = entity_embeddings.device
         nanflag = torch.zeros(1, dtype=torch.int32, device=dev)
         out_entity_1, out_relation_1 = self.sparse_gat_1(
@@ -142,7 +166,10 @@ class SpKBGATModified(nn.Module):
     def forward(self, Corpus_, batch_entities, adj, train_indices_nhop, dropout_masks=None):
         graph = self.prepare_graph(adj, train_indices_nhop)
         # models.py:160-161 -- the parameter itself is overwritten with its row-normalised value
-        SF.rownorm_(self.entity_embeddings.data)
+        # (rebinds .data to a fresh tensor like the reference does, so a tensor the caller shares with the Parameter and
+        # anything an earlier forward saved for backward are left untouched)
+        with torch.cuda.device(self.entity_embeddings.device):
+            self.entity_embeddings.data = SF.rownorm(self.entity_embeddings.data)
         out_entity_1, out_relation_1, mask = self._run(self.entity_embeddings, self.relation_embeddings,
                                                        batch_entities, graph, dropout_masks)
         self.final_entity_embeddings.data = out_entity_1.data                                         # 181

@@ -157,3 +157,14 @@ def test_load_embed_array_other_json_layouts_and_errors(tmp_path):
         load_embed_array(str(tmp_path / "bad.json"))
     with pytest.raises(RuntimeError):
         load_embed_array(str(tmp_path / "missing.json"))
+
+
+def test_load_embed_array_rejects_duplicate_and_overlong_keys(tmp_path):
+    """A repeated key leaves another row unwritten and a 20-digit key overflows int64: both must fail, not corrupt memory."""
+    from recon_b200.export import load_embed_array
+    (tmp_path / "dup.json").write_text('{"0": [1.0, 2.0], "0": [3.0, 4.0]}')
+    with pytest.raises(RuntimeError):
+        load_embed_array(str(tmp_path / "dup.json"))
+    (tmp_path / "long.json").write_text('{"18446744073709551616": [1.0, 2.0], "1": [3.0, 4.0]}')
+    with pytest.raises(RuntimeError):
+        load_embed_array(str(tmp_path / "long.json"))

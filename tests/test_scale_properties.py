@@ -62,7 +62,8 @@ def _compact(edge, etype, nhop, sub_mask, n):
 
 
 @pytest.mark.parametrize("n,e1,e2,r,hub_frac", [(2_000_000, 20_000_000, 0, 1000, 0.2),        # C2 (BASELINE configs[1])
-                                                (500_000, 4_000_000, 8_000_000, 1000, 0.2)])  # C3's 1:2 hop mix, quarter size
+                                                (500_000, 4_000_000, 8_000_000, 1000, 0.2),   # C3's 1:2 hop mix, quarter size
+                                                (2_000_000, 20_000_000, 40_000_000, 1000, 0.2)])  # C3 (configs[2]), full size
 def test_full_size_locality_parity(n, e1, e2, r, hub_frac):
     from recon_b200 import SpKBGATModified
     from recon_b200.synth import make_kg
@@ -136,3 +137,167 @@ def test_full_size_locality_parity(n, e1, e2, r, hub_frac):
     assert torch.equal(out_e, out_e2) and torch.equal(out_r, out_r2)
     for k in grads:
         assert torch.equal(grads[k], grads2[k]), k
+
+
+def _giant_hub_kg(n, r, hub_deg, background, seed):
+    """One aggregation row with `hub_deg` in-edges (gathered nodes and relations uniform) shuffled into a Zipf background."""
+    from recon_b200.synth import make_kg
+    g = torch.Generator().manual_seed(seed)
+    edge_b, et_b, _ = make_kg(n, background, r, 1.1, 0, seed=seed, hub_frac=0.2)
+    hub = 7
+    rows = torch.full((hub_deg,), hub, dtype=torch.int64)
+    cols = torch.randint(0, n, (hub_deg,), generator=g)
+    et_h = torch.randint(0, r, (hub_deg,), generator=g)
+    perm = torch.randperm(hub_deg + background, generator=g)
+    edge = torch.cat((torch.stack((rows, cols)), edge_b), dim=1)[:, perm].contiguous()
+    etype = torch.cat((et_h, et_b))[perm].contiguous()
+    return edge, etype, hub
+
+
+def _hub_case(n, r, edge, etype, seed, bwd_mode=None):
+    """CUDA path vs the fp64 oracle on the whole graph: outputs + every gradient, rel-L2."""
+    from recon_b200 import SpKBGATModified
+    from recon_b200 import functional as SF
+    from oracle import ref_torch as O
+    p = O.init_params(n, r, F_IN, D_OUT, HEADS, seed=seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    g_ent = torch.randn(n, D_OUT * HEADS, generator=gen)
+    g_rel = torch.randn(r, D_OUT * HEADS, generator=gen)
+    model = SpKBGATModified(p["entity_embeddings"].clone(), p["relation_embeddings"].clone(), [D_OUT, 2 * D_OUT],
+                            [D_OUT, 2 * D_OUT], 0.0, ALPHA, [HEADS, HEADS], None)
+    model.load_state_dict(p)
+    model = model.to(dev())
+    graph = model.prepare_graph((edge.to(dev()), etype.to(dev())), None)
+    saved = SF.BWD_MODE
+    try:
+        if bwd_mode:
+            SF.BWD_MODE = bwd_mode
+        out_e, out_r, _ = model(None, torch.arange(n), graph, None)
+        ((out_e * g_ent.to(dev())).sum() + (out_r * g_rel.to(dev())).sum()).backward()
+        torch.cuda.synchronize()
+    finally:
+        SF.BWD_MODE = saved
+    q = {k: v.double() for k, v in p.items()}
+    ref = O.fwd_bwd(q, torch.arange(n), (edge, etype), None, ALPHA, g_ent.double(), g_rel.double(), None, O.seg_sum_index_add)
+    errs = {"out_entity": rel_l2(out_e, ref[0]), "out_relation": rel_l2(out_r, ref[1])}
+    for nm, prm in model.named_parameters():
+        if nm in ref[4] and prm.grad is not None:
+            errs["grad." + nm] = rel_l2(prm.grad, ref[4][nm])
+    assert len(errs) >= 12
+    return graph, errs
+
+
+def test_giant_hub_row_long_tasks_parity():
+    """C5's defining feature (BASELINE configs[4]: hub entities of > 1M in-degree): a row of 1.15M in-edges exceeds
+    HUB_MAX_TASKS * HUB_CHUNK = 1,048,576, so HubSet (recon_b200/graph.py) cuts it into tasks LONGER than 256 edges. The
+    whole graph (1.25M edges) still fits the fp64 oracle, so this is a direct check of forward, all three backward
+    schedules' hub branches (row / column / relation tasks + fixed-order finalize) against GAT/layers.py:150-169."""
+    import psutil
+    if psutil.virtual_memory().available < 40 * 2 ** 30:
+        pytest.skip("the fp64 oracle needs ~22 GB of host memory for this case")
+    from recon_b200 import graph as G
+    n, r = 20000, 40
+    edge, etype, hub = _giant_hub_kg(n, r, 1_150_000, 100_000, seed=3)
+    graph, errs = _hub_case(n, r, edge, etype, seed=5)
+    h = graph.row_hubs
+    lens = (h.task_end - h.task_beg)
+    assert int(lens.max()) > G.HUB_CHUNK and h.n_tasks <= G.HUB_MAX_TASKS + 64 * h.n_hubs      # the long-task branch ran
+    assert graph.rel_hubs.n_hubs == r                                                           # every relation is a hub segment
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("bwd_mode", ["split", "fused", "rows"])
+def test_hub_long_tasks_small_budget(bwd_mode, monkeypatch):
+    """Same branch at 60k edges by lowering HUB_MAX_TASKS (test hook): tasks of ~1000 edges in all three backward
+    schedules, cheap enough to run every schedule against the oracle."""
+    from recon_b200 import graph as G
+    monkeypatch.setattr(G, "HUB_MAX_TASKS", 64)
+    n, r = 4000, 11
+    edge, etype, hub = _giant_hub_kg(n, r, 60_000, 30_000, seed=13)
+    graph, errs = _hub_case(n, r, edge, etype, seed=15, bwd_mode=bwd_mode)
+    lens = graph.row_hubs.task_end - graph.row_hubs.task_beg
+    assert int(lens.max()) > G.HUB_CHUNK
+    bad = {k: e for k, e in errs.items() if not e < TOL}
+    assert not bad, bad
+
+
+def test_c5_shape_giant_hub_consistency():
+    """BASELINE configs[4] at full size (N=5M, E=100M, every row Pareto(1.1): the top row holds ~53M edges). No CPU oracle
+    holds it; size-independent properties instead: (1) the hub row's forward output equals an independent evaluation of
+    GAT/layers.py:150-169 for that single row, computed in fp64 with plain torch ops on the device from the layer-1
+    output (chunked over the row's edges); (2) re-chunking the hub tasks (HUB_MAX_TASKS 4096 -> 1024, i.e. different
+    task lengths and a different fixed-order tree) changes outputs and gradients by <= 1e-5; (3) reruns are bit-identical."""
+    from recon_b200 import SpKBGATModified
+    from recon_b200 import graph as G
+    from recon_b200.synth import make_kg
+    n, e, r = 5_000_000, 100_000_000, 1000
+    edge, etype, _ = make_kg(n, e, r, 1.1, 0, seed=0, device=dev(), hub_frac=1.0)
+    deg = torch.bincount(edge[0], minlength=n)
+    hub = int(deg.argmax()); hub_deg = int(deg.max())
+    assert hub_deg > 1_100_000
+    del deg
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(0)
+    model = SpKBGATModified(torch.randn(n, F_IN, generator=gen), torch.randn(r, F_IN, generator=gen), [D_OUT, 2 * D_OUT],
+                            [D_OUT, 2 * D_OUT], 0.0, ALPHA, [HEADS, HEADS], None).to(dev())
+    g_ent = torch.randn(n, D_OUT * HEADS, generator=gen).to(dev())
+    g_rel = torch.randn(r, D_OUT * HEADS, generator=gen).to(dev())
+    batch = torch.arange(n, device=dev())
+
+    def run(graph):
+        model.zero_grad(set_to_none=True)
+        out_e, out_r, _ = model(None, batch, graph, None)
+        (torch.dot(out_e.reshape(-1), g_ent.reshape(-1)) + torch.dot(out_r.reshape(-1), g_rel.reshape(-1))).backward()
+        torch.cuda.synchronize()
+        grads = {k: v.grad.detach().clone() for k, v in model.named_parameters() if v.grad is not None}
+        return out_e.detach().clone(), out_r.detach().clone(), grads
+
+    graph = G.KGraph(edge, etype, None, n, r, device=dev())
+    lens = graph.row_hubs.task_end - graph.row_hubs.task_beg
+    assert int(lens.max()) > G.HUB_CHUNK                       # > 1.05M edges: long tasks
+    out_e, out_r, grads = run(graph)
+    out_e2, out_r2, grads2 = run(graph)
+    assert torch.equal(out_e, out_e2) and all(torch.equal(grads[k], grads2[k]) for k in grads)
+    del out_e2, out_r2, grads2
+
+    # (1) the hub row of layer 2, recomputed in fp64 from the layer-1 output x1 (captured through a hook-free re-run)
+    sg = model.sparse_gat_1
+    with torch.no_grad():
+        from recon_b200 import functional as SF
+        nanflag = torch.zeros(1, dtype=torch.int32, device=dev())
+        ent = model.entity_embeddings.detach()
+        x1 = SF.attention_group(ent, model.relation_embeddings.detach(), [a.a for a in sg.attentions],
+                                [a.a_2 for a in sg.attentions], graph, ALPHA, True, None, nanflag)
+        rel1 = (model.relation_embeddings.detach().double() @ sg.W.detach().double())
+        a, a2 = sg.out_att.a.detach().double(), sg.out_att.a_2.detach().double()
+        F2 = x1.shape[1]
+        A1, A2, A3 = a[:, :F2], a[:, F2:2 * F2], a[:, 2 * F2:]
+        sel = (edge[0] == hub).nonzero().flatten()
+        xi = x1[hub].double()
+        p1 = A1 @ xi
+        num = torch.zeros(a.shape[0], dtype=torch.float64, device=dev()); den = torch.zeros((), dtype=torch.float64, device=dev())
+        for c in range(0, sel.numel(), 2_000_000):
+            s = sel[c:c + 2_000_000]
+            m = p1.unsqueeze(0) + x1[edge[1, s]].double() @ A2.t() + rel1[etype[s]] @ A3.t()      # [chunk, D]
+            ee = torch.exp(-torch.nn.functional.leaky_relu((m @ a2.t()).squeeze(1), ALPHA))
+            num += (ee.unsqueeze(1) * m).sum(0); den += ee.sum()
+        h2 = torch.nn.functional.elu(num / den)
+        ew = ent[hub].double() @ model.W_entities.detach().double()
+        ref_row = torch.nn.functional.normalize((ew + h2).unsqueeze(0), dim=1).squeeze(0)
+        assert rel_l2(out_e[hub], ref_row) < TOL
+
+    # (2) different task lengths / finalize tree
+    old = G.HUB_MAX_TASKS
+    try:
+        G.HUB_MAX_TASKS = 1024
+        graph_b = G.KGraph(edge, etype, None, n, r, device=dev())
+    finally:
+        G.HUB_MAX_TASKS = old
+    assert graph_b.row_hubs.n_tasks != graph.row_hubs.n_tasks
+    del graph
+    out_b, out_rb, grads_b = run(graph_b)
+    errs = {"out_entity": rel_l2(out_b, out_e), "out_relation": rel_l2(out_rb, out_r)}
+    errs.update({"grad." + k: rel_l2(grads_b[k], grads[k]) for k in grads})
+    bad = {k: v for k, v in errs.items() if not v < 1e-5}
+    assert not bad, bad
