@@ -408,8 +408,8 @@ class SingleGPU:
         ent = torch.randn(n, F_IN, generator=g)
         rel = torch.randn(r, F_IN, generator=g)
         self.model = SpKBGATModified(ent, rel, [D_OUT, 2 * D_OUT], [D_OUT, 2 * D_OUT], 0.0, ALPHA, [HEADS, HEADS], None).to(dev)
-        self.host = (edge.pin_memory(), etype.pin_memory(), nhop.pin_memory())
         self.edge, self.etype, self.nhop = edge.to(dev), etype.to(dev), nhop.to(dev)
+        self._host = None if edge.is_cuda else (edge.pin_memory(), etype.pin_memory(), nhop.pin_memory())
         self.batch = torch.arange(n, device=dev)
         self.g_ent = torch.randn(n, D_OUT * HEADS, generator=g).to(dev)
         self.g_rel = torch.randn(r, D_OUT * HEADS, generator=g).to(dev)
@@ -424,6 +424,13 @@ class SingleGPU:
         loss = torch.dot(out_e.reshape(-1), self.g_ent.reshape(-1)) + torch.dot(out_r.reshape(-1), self.g_rel.reshape(-1))
         loss.backward()
         return loss
+
+    @property
+    def host(self):
+        """Pinned host copies of the int64 edge tensors (the form the reference's data pipeline hands over)."""
+        if self._host is None:
+            self._host = tuple(t.cpu().pin_memory() for t in (self.edge, self.etype, self.nhop))
+        return self._host
 
     def graph_build_ms(self, reps=3):
         """CSR + CSC + relation layouts from the device-resident int64 edge tensors (per graph, amortised over epochs;
