@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* spk_stream_t;              /* cudaStream_t */
 
-#define SPK_ABI_VERSION 3
+#define SPK_ABI_VERSION 4
 int spk_abi_version(void);
 const char* spk_last_error(void);
 int64_t spk_launch_count(void);          /* kernels launched through this library so far */
@@ -173,14 +173,21 @@ int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* args, spk_stream_t st
 /* ---- K3"/K4": the same backward for graphs without 2-hop edges, with the per-edge dot t = dnum_i . m_e split between the
  *      column pass (dnum_i . P2[j], P2~[j] in registers) and the relation pass (dnum_i . P3[k], P3~[k] in registers), the two
  *      passes that gather dnum_i anyway: no projected row is gathered per edge at all. Computes G, dP1~, dP2~ AND dP3~.
- *      rec4 [E, H, 4] and dsv [E, H] are scratch in CSR order. ---- */
+ *      rec4 [E, H, 4] and dsv [E, H] are scratch in CSR order.
+ *      `phases` (0 = all) selects what one call launches, so that a multi-GPU caller can start the reduce-scatter of the
+ *      partial dP2~ right after the column pass and overlap it with the rest:
+ *        1 = node pass + column pass (G, rowsc, dP1~ without its q slot, rec4, dP2~ without its q slot)
+ *        2 = relation pass (dsv, dP3~) + row sums of ds (q slot of dP1~)
+ *        4 = column sums of ds: into the q slot of dP2~, or, when `colsum` is given, into colsum[col * ld_colsum + h]
+ *      Phases must run in the order 1, 2, 4 on one stream. ---- */
 typedef struct {
     spk_edge_bwd_fused_args base;                /* csc_t2 must be null; rec unused; col_hub as there; row_hub.partial [n_tasks, >= 4] */
     const int32_t* relptr; const int32_t* rel_row; const int32_t* rel_pos;
     float* rec4; float* dsv;
     float* dP3; int64_t ldd3;                    /* [n_rel, width] */
-    int32_t n_rel; int32_t reserved;
+    int32_t n_rel; int32_t phases;
     spk_hub_tasks rel_hub;                       /* relation segments as tasks; partial [n_tasks, ldpart >= width] */
+    float* colsum; int64_t ld_colsum;            /* optional [n_cols, ld_colsum >= n_heads] destination of phase 4 */
 } spk_edge_bwd_split_args;
 int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* args, spk_stream_t stream);
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f32p = C.POINTER(C.c_float)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class Geom(C.Structure):
@@ -82,8 +82,9 @@ class EdgeBwdSplitArgs(C.Structure):
                 ("relptr", C.c_void_p), ("rel_row", C.c_void_p), ("rel_pos", C.c_void_p),
                 ("rec4", C.c_void_p), ("dsv", C.c_void_p),
                 ("dP3", C.c_void_p), ("ldd3", C.c_int64),
-                ("n_rel", C.c_int32), ("reserved", C.c_int32),
-                ("rel_hub", HubTasks)]
+                ("n_rel", C.c_int32), ("phases", C.c_int32),
+                ("rel_hub", HubTasks),
+                ("colsum", C.c_void_p), ("ld_colsum", C.c_int64)]
 
 
 class AggGeom(C.Structure):

@@ -423,24 +423,33 @@ int launch_split_pass(const BwdSplitArgs& a, cudaStream_t s, int which) {
 
 template <int NCH, int HT>
 int launch_split_t(const BwdSplitArgs& a, cudaStream_t s) {
-    if (int rc = launch_edge_bwd_node(a.f, s)) return rc;
-    if (int rc = launch_split_pass<NCH, HT>(a, s, 0)) return rc;
-    if (a.col_hub.n_tasks > 0) {
-        SegGatherArgs fa;
-        fa.segptr = a.colptr; fa.src = nullptr; fa.pos = nullptr; fa.G = a.G; fa.ldg = a.ldg; fa.rec = nullptr;
-        fa.outp = a.dP2; fa.ldout = a.ldd2; fa.n_seg = a.n_cols; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.col_hub;
-        if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
+    if (a.phases & 1) {
+        if (int rc = launch_edge_bwd_node(a.f, s)) return rc;
+        if (int rc = launch_split_pass<NCH, HT>(a, s, 0)) return rc;
+        if (a.col_hub.n_tasks > 0) {
+            SegGatherArgs fa;
+            fa.segptr = a.colptr; fa.src = nullptr; fa.pos = nullptr; fa.G = a.G; fa.ldg = a.ldg; fa.rec = nullptr;
+            fa.outp = a.dP2; fa.ldout = a.ldd2; fa.n_seg = a.n_cols; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.col_hub;
+            if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
+        }
     }
-    if (int rc = launch_split_pass<NCH, HT>(a, s, 1)) return rc;
-    if (a.rel_hub.n_tasks > 0) {
-        SegGatherArgs fa;
-        fa.segptr = a.relptr; fa.src = nullptr; fa.pos = nullptr; fa.G = a.G; fa.ldg = a.ldg; fa.rec = nullptr;
-        fa.outp = a.dP3; fa.ldout = a.ldd3; fa.n_seg = a.n_rel; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.rel_hub;
-        if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
+    if (a.phases & 2) {
+        if (int rc = launch_split_pass<NCH, HT>(a, s, 1)) return rc;
+        if (a.rel_hub.n_tasks > 0) {
+            SegGatherArgs fa;
+            fa.segptr = a.relptr; fa.src = nullptr; fa.pos = nullptr; fa.G = a.G; fa.ldg = a.ldg; fa.rec = nullptr;
+            fa.outp = a.dP3; fa.ldout = a.ldd3; fa.n_seg = a.n_rel; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.rel_hub;
+            if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
+        }
+        // q slot of dP1~ (rows: contiguous records)
+        if (int rc = launch_sums<HT>(a.f.rowptr, nullptr, a.dsv, a.g.H, a.f.n_rows, a.f.row_hub, a.f.dP1, a.f.ldd1, a.g.Dt4 * 4, s)) return rc;
     }
-    // q slots of dP1~ (rows: contiguous records) and dP2~ (columns: records through csc_pos)
-    if (int rc = launch_sums<HT>(a.f.rowptr, nullptr, a.dsv, a.g.H, a.f.n_rows, a.f.row_hub, a.f.dP1, a.f.ldd1, a.g.Dt4 * 4, s)) return rc;
-    return launch_sums<HT>(a.colptr, a.csc_pos, a.dsv, a.g.H, a.n_cols, a.col_hub, a.dP2, a.ldd2, a.g.Dt4 * 4, s);
+    if (a.phases & 4) {
+        // q slot of dP2~ (columns: records through csc_pos), or the caller's separate column-sum array
+        if (a.colsum) return launch_sums<HT>(a.colptr, a.csc_pos, a.dsv, a.g.H, a.n_cols, a.col_hub, a.colsum, a.ld_colsum, 0, s);
+        return launch_sums<HT>(a.colptr, a.csc_pos, a.dsv, a.g.H, a.n_cols, a.col_hub, a.dP2, a.ldd2, a.g.Dt4 * 4, s);
+    }
+    return 0;
 }
 
 template <int NCH>

@@ -65,6 +65,13 @@ class RowPartition:
         return e_loc, t_loc, nh_loc, sel1, sel2
 
 
+class _Done:
+    """Handle of an exchange that already completed (gloo path)."""
+
+    def wait(self):
+        return True
+
+
 class DistContext:
     """Collectives of the partitioned path; attached to a KGraph as `graph.dist`."""
 
@@ -79,31 +86,65 @@ class DistContext:
         lo, hi = self.part.rows_of(self.rank)
         return hi - lo
 
+    # ---- zero-copy exchange buffers -------------------------------------------------------------------------------
+    # The gathered table of a layer lives in ONE buffer [world * max_rows, W] in padded global numbering. The producer
+    # kernel (GEMM epilogue / table builder) writes this rank's rows straight into its slot, the all-gather runs in place,
+    # and the reduce-scatter of a partial gradient lands in a [max_rows, W] buffer whose first n_local rows are the result:
+    # no pad / slice / contiguous copies around the collectives. Both collectives are started asynchronously (NCCL's own
+    # stream) and return a handle whose wait() orders the current stream after them, so independent kernels overlap.
+
+    def gather_buffer(self, width, device, dtype=torch.float32):
+        """([world * max_rows, width] buffer, view of this rank's n_local rows inside it). Pad rows of the own slot are zero."""
+        mr = self.part.max_rows
+        buf = torch.empty(self.world * mr, width, dtype=dtype, device=device)
+        lo = self.rank * mr
+        if self.n_local < mr:
+            buf[lo + self.n_local:lo + mr].zero_()
+        return buf, buf[lo:lo + self.n_local]
+
+    def all_gather_start(self, buf):
+        """In-place all-gather of every rank's slot of `buf`; returns a handle with wait()."""
+        mr = self.part.max_rows
+        mine = buf[self.rank * mr:(self.rank + 1) * mr]
+        if dist.get_backend(self.group) == "gloo":           # gloo: no aliasing of input and output
+            dist.all_gather_into_tensor(buf, mine.clone(), group=self.group)
+            return _Done()
+        return dist.all_gather_into_tensor(buf, mine, group=self.group, async_op=True)
+
+    def reduce_scatter_start(self, partial_all, out_pad):
+        """Sum over ranks of the [world * max_rows, W] partials; this rank's slot lands in out_pad [max_rows, W]."""
+        assert partial_all.is_contiguous() and out_pad.is_contiguous() and out_pad.shape[0] == self.part.max_rows
+        if dist.get_backend(self.group) == "gloo":           # gloo has no reduce_scatter: all-reduce and slice
+            full = partial_all.clone()
+            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
+            out_pad.copy_(full[self.rank * self.part.max_rows:(self.rank + 1) * self.part.max_rows])
+            return _Done()
+        return dist.reduce_scatter_tensor(out_pad, partial_all, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def all_gather_rows(self, local_rows):
-        """[n_local, W] (any row stride) -> [world * max_rows, W] in padded global numbering."""
-        w = local_rows.shape[1]
-        pad = local_rows.new_zeros(self.part.max_rows, w)
-        pad[: local_rows.shape[0]] = local_rows
-        out = local_rows.new_empty(self.world * self.part.max_rows, w)
-        dist.all_gather_into_tensor(out, pad, group=self.group)
-        return out
+        """[n_local, W] (any row stride) -> [world * max_rows, W] in padded global numbering (copying convenience form)."""
+        buf, mine = self.gather_buffer(local_rows.shape[1], local_rows.device, local_rows.dtype)
+        mine.copy_(local_rows)
+        self.all_gather_start(buf).wait()
+        return buf
 
     def reduce_scatter_rows(self, partial_all, out_local):
         """Sum over ranks of [world * max_rows, W] partials; this rank's rows land in out_local [n_local, W]."""
-        w = partial_all.shape[1]
-        if dist.get_backend(self.group) == "gloo":           # gloo has no reduce_scatter: all-reduce and slice
-            full = partial_all.contiguous().clone()
-            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
-            chunk = full[self.rank * self.part.max_rows:(self.rank + 1) * self.part.max_rows]
-        else:
-            chunk = partial_all.new_empty(self.part.max_rows, w)
-            dist.reduce_scatter_tensor(chunk, partial_all.contiguous(), op=dist.ReduceOp.SUM, group=self.group)
-        out_local.copy_(chunk[: out_local.shape[0]])
+        pad = partial_all.new_empty(self.part.max_rows, partial_all.shape[1])
+        self.reduce_scatter_start(partial_all.contiguous(), pad).wait()
+        out_local.copy_(pad[: out_local.shape[0]])
         return out_local
 
     def all_reduce(self, t):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def all_reduce_start(self, t):
+        """Asynchronous all-reduce (sum) of a small replicated gradient; returns a handle with wait()."""
+        if dist.get_backend(self.group) == "gloo":
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return _Done()
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
 
 class PartitionedKBGAT:

@@ -222,8 +222,12 @@ def _fill_fused_args(f, graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out
     return part
 
 
-def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, sw, dP1, dP2, dP3):
-    """Backward edge passes. Fills dP1 [n_rows, Wd], dP2 [n_cols, Wd] (indexed by gathered node) and dP3 [R, Wd]."""
+def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out, dout, den, sw, dP1, dP2, dP3,
+                       after_columns=None, colsum=None):
+    """Backward edge passes. Fills dP1 [n_rows, Wd], dP2 [n_cols, Wd] (indexed by gathered node) and dP3 [R, Wd].
+    Multi-GPU hook: `after_columns()` is called as soon as dP2 is complete except for its q slot (the column sums of ds,
+    which need the relation pass); those sums then go to `colsum` [n_cols, H]. Returns True when that split happened,
+    False when dP2 came out complete in one piece (schedules other than "split")."""
     lib = _lib.load()
     graph.build_backward()
     n, dev = graph.n_nodes, P1.device
@@ -247,9 +251,21 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
         graph.rel_hubs.fill(q.rel_hub, part3, geom.Wd)
         part1 = _hub_partial(graph.row_hubs, 4, dev)                # row sums of ds over hub rows
         graph.row_hubs.fill(q.base.row_hub, part1, 4)
+        if after_columns is None:
+            _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+            del keep, part3, part1
+            return False
+        q.phases = 1
+        _lib.current_tag = "cols"
         _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+        after_columns()
+        q.phases = 6
+        q.colsum = colsum.data_ptr(); q.ld_colsum = colsum.stride(0)
+        _lib.current_tag = "rels"
+        _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+        _lib.current_tag = ""
         del keep, part3, part1
-        return
+        return True
     rec = torch.empty(ne, 2 * geom.H, dtype=torch.float32, device=dev)
     if mode == "fused":
         f = _lib.EdgeBwdFusedArgs()
@@ -259,7 +275,7 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
         _lib.check(lib.spk_edge_attn_bwd_fused(C.byref(f), _lib.stream_ptr()), "edge_attn_bwd_fused")
         del keep
         seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, G, ldg, rec, geom, dP3, graph.n_rel, "rels")
-        return
+        return False
     a = _lib.EdgeBwdRowsArgs()
     a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
     a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
@@ -280,6 +296,7 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
 
     seg_gather(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, G, ldg, rec, geom, dP2, graph.n_cols, "cols")
     seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, G, ldg, rec, geom, dP3, graph.n_rel, "rels")
+    return False
 
 
 def seg_gather(ptr, src, pos, hubs, G, ldg, rec, geom, dst, n_seg, tag):
@@ -314,22 +331,33 @@ class AttentionGroupFn(torch.autograd.Function):
         X = tc_friendly(X.contiguous()); Wn = Wn.contiguous(); Rel = Rel.contiguous(); Wr = Wr.contiguous()
         dist = getattr(graph, "dist", None)
         Wd = geom.Wd
-        P3 = gemm_nn(Rel, Wr)                   # [R, Wd]
         mode = "local"
         X_all = None
         if dist is None:
+            P3 = gemm_nn(Rel, Wr)               # [R, Wd]
             P = gemm_nn(X, Wn)                  # [N, 2Wd] = [P1~ | P2~]
             P1, P2 = P[:, :Wd], P[:, Wd:]
         elif 2 * X.shape[1] <= Wd:
-            mode = "input"
-            X_all = tc_friendly(dist.all_gather_rows(X))
+            mode = "input"                      # every rank projects all nodes from the gathered input rows
+            Fp = (X.shape[1] + 3) // 4 * 4
+            X_all, mine = dist.gather_buffer(Fp, X.device)
+            mine[:, :X.shape[1]].copy_(X)
+            if Fp != X.shape[1]:
+                mine[:, X.shape[1]:].zero_()
+            h = dist.all_gather_start(X_all)
+            P3 = gemm_nn(Rel, Wr)
             P1 = gemm_nn(X, Wn[:, :Wd])
-            P2 = gemm_nn(X_all, Wn[:, Wd:])     # every rank projects all nodes
+            h.wait()
+            X_all = X_all[:, :X.shape[1]]
+            P2 = gemm_nn(X_all, Wn[:, Wd:])
         else:
-            mode = "proj"
-            P = gemm_nn(X, Wn)
-            P1 = P[:, :Wd]
-            P2 = dist.all_gather_rows(P[:, Wd:])
+            mode = "proj"                       # the GEMM writes this rank's P2~ rows straight into the exchange buffer
+            P2, mine = dist.gather_buffer(Wd, X.device)
+            gemm_nn(X, Wn[:, Wd:], out=mine)
+            h = dist.all_gather_start(P2)       # in flight while P1~ and P3~ are projected
+            P1 = gemm_nn(X, Wn[:, :Wd])
+            P3 = gemm_nn(Rel, Wr)
+            h.wait()
         out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
         ctx.save_for_backward(X, Wn, Rel, Wr, P1, P2, P3, out, den, sw, X_all if X_all is not None else X.new_empty(0))
         ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, ctx.mode = graph, geom, alpha, apply_elu, mask_csr, mode
@@ -344,47 +372,82 @@ class AttentionGroupFn(torch.autograd.Function):
         Wd = geom.Wd
         dout = dout.contiguous()
         n = X.shape[0]
+        dev = X.device
         dP3 = torch.empty_like(P3)
         WnT = Wn.t().contiguous()               # [2Wd, F]
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dX = dWn = None
         if mode == "local":
-            dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=X.device)
+            dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=dev)
             edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
                                dP[:, :Wd], dP[:, Wd:], dP3)
             if need_x:
                 dX = gemm_nn(dP, WnT)
             if need_w:
                 dWn = gemm_tn(X, dP)
-        elif mode == "proj":
-            dP = torch.empty(n, 2 * Wd, dtype=torch.float32, device=X.device)
-            dP2_all = torch.empty_like(P2)      # partial over this rank's edges, all gathered nodes
-            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
-                               dP[:, :Wd], dP2_all, dP3)
-            dist.reduce_scatter_rows(dP2_all, dP[:, Wd:])
-            del dP2_all
-            dist.all_reduce(dP3)
-            if need_x:
-                dX = gemm_nn(dP, WnT)
-            if need_w:
-                dWn = dist.all_reduce(gemm_tn(X, dP))
-        else:                                   # "input"
-            dP1 = torch.empty(n, Wd, dtype=torch.float32, device=X.device)
+        else:
+            # partial dP2~ over this rank's edges for ALL gathered nodes -> owners. "proj": reduce-scatter the projected
+            # rows; "input": project the partial back to input space first (F < Wd floats per node over NVLink).
+            # The reduce-scatter starts right after the column pass and runs under the relation pass and the products
+            # that only need dP1~.
+            mr = dist.part.max_rows
+            dP1 = torch.empty(n, Wd, dtype=torch.float32, device=dev)
             dP2_all = torch.empty_like(P2)
-            edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
-                               dP1, dP2_all, dP3)
-            dist.all_reduce(dP3)
-            if need_x:
-                dX2_all = gemm_nn(dP2_all, WnT[Wd:])            # partial dX of every node through the gathered side
-                dX = torch.empty(n, X.shape[1], dtype=torch.float32, device=X.device)
-                dist.reduce_scatter_rows(dX2_all, dX)
-                del dX2_all
-                gemm_nn(dP1, WnT[:Wd], out=dX, accumulate=True)
-            if need_w:
-                dWn = torch.empty_like(Wn)
-                gemm_tn(X, dP1, out=dWn[:, :Wd])
-                gemm_tn(X_all, dP2_all, out=dWn[:, Wd:])
-                dist.all_reduce(dWn)
+            colsum = torch.empty(P2.shape[0], geom.H, dtype=torch.float32, device=dev)
+            pend = {}
+
+            def start_main():
+                if mode == "proj":
+                    pend["pad"] = torch.empty(mr, Wd, dtype=torch.float32, device=dev)
+                    pend["h"] = dist.reduce_scatter_start(dP2_all, pend["pad"])
+
+            split = edge_attn_backward(graph, P1, P2, P3, geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, out, dout, den, sw,
+                                       dP1, dP2_all, dP3, after_columns=start_main if mode == "proj" else None, colsum=colsum)
+            if mode == "proj":
+                if split:
+                    qs_pad = torch.empty(mr, geom.H, dtype=torch.float32, device=dev)
+                    hq = dist.reduce_scatter_start(colsum, qs_pad)
+                else:
+                    start_main()
+                h3 = dist.all_reduce_start(dP3)
+                if need_x:
+                    dX = gemm_nn(dP1, WnT[:Wd])
+                if need_w:
+                    dWn = torch.empty_like(Wn)
+                    gemm_tn(X, dP1, out=dWn[:, :Wd])
+                pend["h"].wait()
+                dP2 = pend["pad"][:n]
+                if split:
+                    hq.wait()
+                    dP2[:, geom.Dt:geom.Dt + geom.H].copy_(qs_pad[:n])
+                del dP2_all
+                if need_x:
+                    gemm_nn(dP2, WnT[Wd:], out=dX, accumulate=True)
+                if need_w:
+                    gemm_tn(X, dP2, out=dWn[:, Wd:])
+                    dist.all_reduce(dWn)
+                h3.wait()
+            else:                               # "input"
+                h3 = dist.all_reduce_start(dP3)
+                F = X.shape[1]
+                Fp = (F + 3) // 4 * 4
+                if need_x:
+                    dX2_all = torch.empty(P2.shape[0], Fp, dtype=torch.float32, device=dev)
+                    gemm_nn(dP2_all, WnT[Wd:], out=dX2_all[:, :F])
+                    if Fp != F:
+                        dX2_all[:, F:].zero_()
+                    pad = torch.empty(mr, Fp, dtype=torch.float32, device=dev)
+                    h = dist.reduce_scatter_start(dX2_all, pad)
+                    dX1 = gemm_nn(dP1, WnT[:Wd])
+                    h.wait()
+                    dX = dX1.add_(pad[:n, :F])
+                    del dX2_all
+                if need_w:
+                    dWn = torch.empty_like(Wn)
+                    gemm_tn(X, dP1, out=dWn[:, :Wd])
+                    gemm_tn(X_all, dP2_all, out=dWn[:, Wd:])
+                    dist.all_reduce(dWn)
+                h3.wait()
         dRel = gemm_nn(dP3, Wr.t().contiguous()) if ctx.needs_input_grad[2] else None
         dWr = gemm_tn(Rel, dP3) if ctx.needs_input_grad[3] else None
         return dX, dWn, dRel, dWr, None, None, None, None, None, None
@@ -449,8 +512,10 @@ def agg_weights(a_list, a2_list, geom):
     return Wa, V, V3
 
 
-def _agg_table(X, V, ld, chunks):
-    T = torch.empty(X.shape[0], ld, dtype=torch.float32, device=X.device)
+def _agg_table(X, V, ld, chunks, out=None):
+    T = torch.empty(X.shape[0], ld, dtype=torch.float32, device=X.device) if out is None else out
+    assert T.shape[0] == X.shape[0] and T.stride(1) == 1 and T.stride(0) >= ld
+    ld = T.stride(0)
     if X.shape[0]:
         _lib.check(_lib.load().spk_agg_table(_lib.ptr(X), X.stride(0), _lib.ptr(V), _lib.ptr(T), ld, X.shape[0],
                                              X.shape[1], chunks, _lib.stream_ptr()), "agg_table")
@@ -468,11 +533,19 @@ class AggGroupFn(torch.autograd.Function):
         n, dev = graph.n_nodes, X.device
         H, D, LZ = geom.H, geom.D, geom.LZ
         dist = getattr(graph, "dist", None)
-        Xt = _agg_table(X, V, geom.LX, geom.Fx4)
-        Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
         # multi-GPU: rows are partitioned, the gathered table must cover all nodes -> all-gather the
-        # X~ rows (LX = 56 floats for F = 50: 3.7x fewer bytes than the projected rows)
-        Xc = dist.all_gather_rows(Xt) if dist is not None else Xt
+        # X~ rows (LX = 56 floats for F = 50: 3.7x fewer bytes than the projected rows). The table builder writes this
+        # rank's rows straight into the exchange buffer; the all-gather runs in place, under the Rel~ table build.
+        if dist is None:
+            Xt = _agg_table(X, V, geom.LX, geom.Fx4)
+            Xc = Xt
+            Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
+        else:
+            Xc, Xt = dist.gather_buffer(geom.LX, dev)
+            _agg_table(X, V, geom.LX, geom.Fx4, out=Xt)
+            hx = dist.all_gather_start(Xc)
+            Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
+            hx.wait()
         Z = torch.empty(n, H * LZ, dtype=torch.float32, device=dev)
         den = torch.empty(n, H, dtype=torch.float32, device=dev)
         sw = torch.empty(n, H, dtype=torch.float32, device=dev)
@@ -543,16 +616,19 @@ class AggGroupFn(torch.autograd.Function):
         dXc = torch.empty(graph.n_cols, gx_geom.Wd, **f32)
         seg_gather(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, Gx, Gx.stride(0), rec, gx_geom, dXc,
                    graph.n_cols, "cols")
+        if dist is not None:                              # partial sums over this rank's edges -> owners: the reduce-
+            dXc_all = dXc                                 # scatter runs under the relation pass
+            dXc_pad = torch.empty(dist.part.max_rows, gx_geom.Wd, **f32)
+            hx = dist.reduce_scatter_start(dXc_all, dXc_pad)
         dRc = torch.empty(graph.n_rel, gr_geom.Wd, **f32)
         seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, Gr, Gr.stride(0), rec, gr_geom, dRc,
                    graph.n_rel, "rels")
-        if dist is not None:                              # partial sums over this rank's edges -> owners / all ranks
-            dXc_all = dXc
-            dXc = torch.empty(n, gx_geom.Wd, **f32)
-            dist.reduce_scatter_rows(dXc_all, dXc)
-            del dXc_all
+        if dist is not None:
             dist.all_reduce(dRc)
             dist.all_reduce(dWa)
+            hx.wait()
+            dXc = dXc_pad[:n]
+            del dXc_all
         dX = torch.empty(n, geom.F, **f32)
         dq = torch.empty(n, 4, **f32)
         _lib.check(lib.spk_agg_dx(_lib.ptr(rowout), rowout.stride(0), _lib.ptr(dXc), dXc.stride(0), _lib.ptr(V), n,
