@@ -378,14 +378,24 @@ def main():
                     r2 = run_config(w, world, rank, dev, 3, 2)
                     if rank == 0:
                         line[w] = secondary(r2, world)
+                        print("[bench] " + w + ": " + json.dumps(line[w]), file=sys.stderr, flush=True)
             except Exception as exc:                 # noqa: BLE001
                 if rank == 0:
                     line[w] = {"error": repr(exc)[:300]}
                 if world > 1:
                     raise
+    if rank == 0:
+        print("[bench] primary: " + json.dumps({k: line[k] for k in ("value", "ms_per_step", "n_gpus")}), file=sys.stderr, flush=True)
     if world > 1 and not args.no_parity:
         from recon_b200.dist import parity_check
-        par = parity_check(dev)
+        try:
+            par = parity_check(dev)
+        except Exception as exc:                     # noqa: BLE001  (a failing rank leaves the others in a collective:
+            par = {"error": repr(exc)[:300]}         #  the watchdog above then prints the line)
+            if rank == 0:
+                line["parity"] = par
+                print(json.dumps(line), flush=True)
+            os._exit(0 if rank == 0 else 1)
         if rank == 0:
             line["parity"] = par
     if rank == 0 and not args.no_cpu_baseline and world == 1:

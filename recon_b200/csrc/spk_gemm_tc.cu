@@ -55,10 +55,31 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// multicast form: the box lands at the same CTA-relative offset, and completes on the same CTA-relative mbarrier, in every
+// CTA of the cluster named in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit that arrives on the same CTA-relative mbarrier of every CTA in `mask` (frees a multicast-filled stage cluster-wide)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
@@ -80,6 +101,8 @@ struct TcParams {
     int act;                                    // epilogue: 0 = none, 1 = ELU (GAT/layers.py:175) on the final value
     int c_tma;                                  // epilogue stores through shared memory + TMA (coalesced 128 B rows)
     int raw_hi;                                 // the MMA reads the raw fp32 tile as "hi" (kind::tf32 ignores the low 13 mantissa bits)
+    int cs;                                     // cluster size (1 or 2): the CTAs of a cluster work on consecutive M tiles of the
+                                                // same N tile in lock-step and share every weight tile by TMA multicast
 };
 
 // ELU(x) = x (x > 0) else expm1(x); same evaluation as the edge kernels (degree-5 polynomial near 0)
@@ -114,13 +137,22 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
     const long m_tiles = (p.M + TC_BM - 1) / TC_BM;
-    const long total = m_tiles * p.n_tiles_n;
+    // Work items are "super tiles": cs consecutive M tiles x one N tile, one per cluster and iteration; the CTA of cluster
+    // rank r takes M tile (super * cs + r) (possibly past the end: its loads are zero-filled and its stores clipped), so all
+    // CTAs of a cluster run the same number of pipeline steps and can share the weight tiles.
+    const int cs = p.cs;
+    const uint32_t crank = cs > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1u);
+    const long total = ((m_tiles + cs - 1) / cs) * p.n_tiles_n;
+    const long first = blockIdx.x / cs, stride = gridDim.x / cs;
+    const uint32_t b_slice = b_tile / (uint32_t)cs;               // bytes of this CTA's share of a weight tile
+    const int b_rows = p.BN / cs;
 
     if (threadIdx.x == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
-        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), 1); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 128); mbar_init(empty(s), (uint32_t)cs); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -130,22 +162,28 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();                                // peers' barriers are initialised before anything arrives
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {                                           // ---- TMA producer
             uint32_t it = 0;
-            for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int m0 = (int)(tile / p.n_tiles_n) * TC_BM, n0 = (int)(tile % p.n_tiles_n) * p.BN;
+            for (long tile = first; tile < total; tile += stride) {
+                const int m0 = (int)((tile / p.n_tiles_n) * cs + crank) * TC_BM, n0 = (int)(tile % p.n_tiles_n) * p.BN;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1u;
-                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_wait(empty(s), ph ^ 1u);                   // every CTA of the cluster has released this stage
                     mbar_arrive_expect_tx(full(s), TC_A_TILE + 2u * b_tile);
                     tma_load_2d(a_hi(s), &tmA, full(s), kb * TC_BK, m0);
-                    tma_load_2d(b_hi(s), &tmBhi, full(s), kb * TC_BK, n0);
-                    tma_load_2d(b_lo(s), &tmBlo, full(s), kb * TC_BK, n0);
+                    if (cs == 1) {
+                        tma_load_2d(b_hi(s), &tmBhi, full(s), kb * TC_BK, n0);
+                        tma_load_2d(b_lo(s), &tmBlo, full(s), kb * TC_BK, n0);
+                    } else {                                        // my 1/cs of the weight tile, delivered to all CTAs
+                        tma_load_2d_mc(b_hi(s) + crank * b_slice, &tmBhi, full(s), kb * TC_BK, n0 + (int)crank * b_rows, cmask);
+                        tma_load_2d_mc(b_lo(s) + crank * b_slice, &tmBlo, full(s), kb * TC_BK, n0 + (int)crank * b_rows, cmask);
+                    }
                 }
             }
         }
@@ -153,7 +191,7 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (lane == 0) {                                           // ---- MMA issuer
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, tl = 0;
-            for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+            for (long tile = first; tile < total; tile += stride, ++tl) {
                 const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
                 mbar_wait(tempty(acc), aph ^ 1u);
                 tc_fence_after();
@@ -174,7 +212,8 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         tc_mma_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
                         tc_mma_tf32(d_tmem, dah + o, dbh + o, idesc, 1u);
                     }
-                    tc_commit(empty(s));                            // frees the smem stage when these MMAs retire
+                    if (cs == 1) tc_commit(empty(s));               // frees the smem stage when these MMAs retire
+                    else tc_commit_mc(empty(s), cmask);             // ... in every CTA of the cluster (their copies refill it)
                 }
                 tc_commit(tfull(acc));                              // accumulator complete -> epilogue
             }
@@ -182,7 +221,7 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp < 6) {                                         // ---- splitter: raw fp32 -> (hi, lo)
         const int t = threadIdx.x - 64;
         uint32_t it = 0;
-        for (long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        for (long tile = first; tile < total; tile += stride) {
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const int s = it % p.stages;
                 const uint32_t ph = (it / p.stages) & 1u;
@@ -213,9 +252,9 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int q = warp & 3;
         const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes + (uint32_t)q * 8192u;
         uint32_t tl = 0, sb = 0;
-        for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+        for (long tile = first; tile < total; tile += stride, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-            const int row0 = (int)(tile / p.n_tiles_n) * TC_BM + q * 32;
+            const int row0 = (int)((tile / p.n_tiles_n) * cs + crank) * TC_BM + q * 32;
             const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
             mbar_wait(tfull(acc), aph);
             tc_fence_after();
@@ -249,7 +288,7 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && row0 < p.M) {                      // (a padding tile past the last row stores nothing)
                     if (p.accumulate)
                         asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
                                      ::"l"(&tmC), "r"(n0 + c0), "r"(row0), "r"(stg) : "memory");
@@ -268,9 +307,9 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else {                                                       // ---- epilogue (warps 6..9), per-thread rows (unaligned C)
         const int q = warp & 3;                                    // TMEM lane quarter this warp may access
         uint32_t tl = 0;
-        for (long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tl) {
+        for (long tile = first; tile < total; tile += stride, ++tl) {
             const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
-            const long row = (tile / p.n_tiles_n) * TC_BM + q * 32 + lane;
+            const long row = ((tile / p.n_tiles_n) * cs + crank) * TC_BM + q * 32 + lane;
             const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
             mbar_wait(tfull(acc), aph);
             tc_fence_after();
@@ -313,6 +352,7 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync_all();                                // no CTA leaves while a peer may still signal its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -365,6 +405,16 @@ int make_map(CUtensorMap* tm, const float* ptr, long rows, long cols, long ld, i
 
 int gemm_tc_ldt(int K) { return (K + 3) / 4 * 4; }
 
+// SPK_TC_CLUSTER=2 enables 2-CTA clusters that share every weight tile by TMA multicast. EXPERIMENTAL, off by default:
+// measured on B200 it gains only 2-3 % on the 416-wide products (the kernel is bound by shared-memory bandwidth, not by the
+// L2 -> SM re-stream of the weights: profiles/README.md, round 2) and the C += (TMA reduce-add) epilogue lost updates on
+// short-K shapes in this mode, so it is never combined with `accumulate`.
+static int tc_cluster() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_TC_CLUSTER"); v = (e && e[0] == '2') ? 2 : 1; }
+    return v;
+}
+
 // SPK_TC_RAW_HI=0 restores the explicit hi rewrite in the splitter (default: the raw tile is the hi operand)
 static int tc_raw_hi() {
     static int v = -1;
@@ -402,29 +452,55 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     if (stages < 1) { set_error("gemm_tc: tile does not fit shared memory"); return 3; }
     const int smem = stages * stage_bytes + staging + 1024;
 
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long m_tiles = (M + TC_BM - 1) / TC_BM;
+    // clusters of 2 share each weight tile (half the L2 -> SM traffic of the re-streamed weights); worth it once every SM
+    // has work either way
+    const int cs = (tc_cluster() == 2 && !accumulate && m_tiles * n_tiles_n >= 2L * sms) ? 2 : 1;
+
     CUtensorMap tmA, tmBhi, tmBlo, tmC;
     if (int rc = make_map(&tmA, A, M, K, lda, TC_BM)) return rc;
-    if (int rc = make_map(&tmBhi, bhi, N, K, ldt, BN)) return rc;
-    if (int rc = make_map(&tmBlo, blo, N, K, ldt, BN)) return rc;
+    if (int rc = make_map(&tmBhi, bhi, N, K, ldt, BN / cs)) return rc;
+    if (int rc = make_map(&tmBlo, blo, N, K, ldt, BN / cs)) return rc;
     if (c_tma) { if (int rc = make_map(&tmC, C, M, N, ldc, 32)) return rc; }
     else tmC = tmA;
 
     TcParams p;
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K; p.BN = BN; p.n_tiles_n = n_tiles_n; p.stages = stages;
     p.accumulate = accumulate; p.act = act;
-    p.c_vec = c_vec; p.c_tma = c_tma; p.raw_hi = tc_raw_hi();
+    p.c_vec = c_vec; p.c_tma = c_tma; p.raw_hi = tc_raw_hi(); p.cs = cs;
     static SmemLimit lim;
     if (lim.ensure(gemm_nn_tc_kernel, 226 * 1024) != cudaSuccess) {
         set_error("gemm_tc: cannot raise dynamic shared memory limit");
         (void)cudaGetLastError();
         return 3;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long total = ((M + TC_BM - 1) / TC_BM) * n_tiles_n;
-    const unsigned grid = (unsigned)(total < sms ? total : sms);
-    gemm_nn_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmA, tmBhi, tmBlo, tmC, p);
+    const long total = ((m_tiles + cs - 1) / cs) * n_tiles_n * cs;      // CTAs' worth of tiles
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)sms / cs * cs); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    long resident = sms;                                                // persistent kernel: exactly one wave of CTAs
+    if (cs > 1) {
+        // a GPC with an odd number of free SMs cannot host a whole pair: ask how many clusters are co-resident (cached per
+        // device: 1 CTA per SM at this shared-memory size, so the answer does not depend on the shape)
+        static int clusters[64] = {};
+        int nc = (dev >= 0 && dev < 64) ? clusters[dev] : 0;
+        if (nc == 0) {
+            if (cudaOccupancyMaxActiveClusters(&nc, gemm_nn_tc_kernel, &cfg) != cudaSuccess || nc < 1) { (void)cudaGetLastError(); nc = sms / cs / 2; }
+            if (dev >= 0 && dev < 64) clusters[dev] = nc;
+        }
+        resident = (long)nc * cs;
+    }
+    unsigned grid = (unsigned)(total < resident ? total : resident);
+    grid = grid / cs * cs;
+    if (grid < (unsigned)cs) grid = (unsigned)cs;
+    cfg.gridDim = dim3(grid);
+    (void)cudaLaunchKernelEx(&cfg, gemm_nn_tc_kernel, tmA, tmBhi, tmBlo, tmC, p);
     return check_launch("gemm_nn_tc");
 }
 

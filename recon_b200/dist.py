@@ -235,7 +235,7 @@ class PartitionedKBGAT:
 
 
 def parity_check(device, group=None, n=20000, e=200000, r=64, n_nhop=0, seed=21, in_dim=50, out_dim=100, nheads=2,
-                 alpha=0.2, zipf=1.1):
+                 alpha=0.2, zipf=1.1, hub_frac=0.2):
     """Multi-GPU parity against the single-GPU path of this library on one small seeded KG ("results
     identical (<= 1e-6 rel) to the 1-GPU run"): every rank runs the row-partitioned step, rank 0 also runs the whole
     graph on its own GPU; returns {"max_rel": worst rel-L2 over out_entity, out_relation and every gradient, ...} on
@@ -243,7 +243,7 @@ def parity_check(device, group=None, n=20000, e=200000, r=64, n_nhop=0, seed=21,
     from .models import SpKBGATModified
     from .synth import make_kg
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    edge, etype, nhop = make_kg(n, e, r, alpha=zipf, n_nhop=n_nhop, seed=seed)
+    edge, etype, nhop = make_kg(n, e, r, alpha=zipf, n_nhop=n_nhop, seed=seed, hub_frac=hub_frac)
     gen = torch.Generator().manual_seed(seed + 1)
     ent = torch.randn(n, in_dim, generator=gen)
     rel = torch.randn(r, in_dim, generator=gen)

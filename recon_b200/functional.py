@@ -604,7 +604,7 @@ class AggGroupFn(torch.autograd.Function):
         a.dz = dZ.data_ptr(); a.ldz = dZ.stride(0)
         a.den = den.data_ptr(); a.sw = sw.data_ptr(); a.dden = dden.data_ptr()
         a.gx = Gx.data_ptr(); a.ldgx = Gx.stride(0); a.gr = Gr.data_ptr(); a.ldgr = Gr.stride(0)
-        rowsc = torch.empty(n, 8, **f32)
+        rowsc = torch.empty(max(1, n), 8, **f32)                # (a rank may own no rows at all)
         a.rowout = rowout.data_ptr(); a.ldro = rowout.stride(0); a.rowsc = rowsc.data_ptr(); a.rec = rec.data_ptr()
         a.n_rows = n; a.alpha = float(ctx.alpha); a.geom = geom.struct()
         part = _hub_partial(graph.row_hubs, 8, dev)

@@ -29,7 +29,8 @@ def main():
         if case == "nhop":
             kw["n_nhop"] = 20000
         elif case == "hub":
-            kw.update(zipf=0.6, seed=23)               # Pareto(0.6): the top row holds most of the edges
+            kw.update(zipf=0.6, seed=23, hub_frac=1.0)  # every row Pareto(0.6): the top row holds a third of the edges and
+                                                       # some ranks own no rows at all
         res = parity_check(dev, **kw)
         if rank == 0:
             print("DIST PARITY", case, res, flush=True)
