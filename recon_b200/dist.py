@@ -19,7 +19,11 @@ import torch.distributed as dist
 def balanced_row_bounds(agg_rows, n_rows, world):
     """Row split points [world+1] such that each part holds ~len(agg_rows)/world edges.
     agg_rows: int64 tensor of aggregation rows (edge[0] of every 1-hop and 2-hop edge)."""
-    deg = torch.bincount(agg_rows, minlength=n_rows)
+    return bounds_from_degrees(torch.bincount(agg_rows, minlength=n_rows), n_rows, world)
+
+
+def bounds_from_degrees(deg, n_rows, world):
+    """Same, from the per-row edge counts (rows whose edges are handled elsewhere carry 0)."""
     cum = torch.cumsum(deg, 0)
     total = int(cum[-1]) if n_rows else 0
     targets = torch.tensor([total * g // world for g in range(1, world)], dtype=cum.dtype, device=cum.device)
@@ -31,12 +35,19 @@ def balanced_row_bounds(agg_rows, n_rows, world):
 
 
 class RowPartition:
-    """Which rows each rank owns, and the padded global numbering of gathered nodes."""
+    """Which rows each rank owns, and the padded global numbering of gathered nodes.
+    `hub_ids`: aggregation rows whose in-degree exceeds the per-rank edge budget ("split hub rows across
+    GPUs with a final fixed-order add"). They keep their owner for everything row-local, but their EDGES are cut into
+    `world` contiguous slices, one per rank; every rank aggregates its slice into a ghost row appended after its own rows
+    (local row id n_local + position in hub_ids), the un-normalised partials are summed over the ranks and the owner takes
+    the result (recon_b200.functional). Every slot of the padded numbering reserves len(hub_ids) rows for them."""
 
-    def __init__(self, bounds):
+    def __init__(self, bounds, hub_ids=None):
         self.bounds = list(bounds)
         self.world = len(bounds) - 1
-        self.max_rows = max(1, max(self.bounds[g + 1] - self.bounds[g] for g in range(self.world)))
+        self.hub_ids = torch.as_tensor(hub_ids if hub_ids is not None else [], dtype=torch.int64).cpu()
+        self.n_ghost = int(self.hub_ids.numel())
+        self.max_rows = max(1, max(self.bounds[g + 1] - self.bounds[g] for g in range(self.world)) + self.n_ghost)
 
     def rows_of(self, rank):
         return self.bounds[rank], self.bounds[rank + 1]
@@ -48,12 +59,39 @@ class RowPartition:
         owner = owner.clamp_(0, self.world - 1)
         return owner * self.max_rows + (idx - b[owner])
 
+    def hub_owner(self):
+        """(owner rank, row index inside the owner) of every hub row."""
+        b = torch.tensor(self.bounds, dtype=torch.int64)
+        owner = (torch.searchsorted(b, self.hub_ids, right=True) - 1).clamp_(0, self.world - 1)
+        return owner, self.hub_ids - b[owner]
+
     def local_edges(self, rank, edge, edge_type, nhop):
         """Edges whose aggregation row is owned by `rank`, in original relative order (1-hop block, 2-hop block),
-        with rows made local and gathered nodes remapped. Returns (edge[2,E1'], type[E1'], nhop[E2',4], sel1, sel2)."""
+        with rows made local and gathered nodes remapped; plus this rank's slice of every hub row's edge list, with
+        the ghost row ids. Returns (edge[2,E1'], type[E1'], nhop[E2',4], sel1, sel2)."""
         lo, hi = self.rows_of(rank)
-        sel1 = ((edge[0] >= lo) & (edge[0] < hi)).nonzero().flatten()
-        e_loc = torch.stack((edge[0, sel1] - lo, self.remap(edge[1, sel1])), dim=0)
+        mine = (edge[0] >= lo) & (edge[0] < hi)
+        if self.n_ghost:
+            hubs = self.hub_ids.to(edge.device)
+            in_hub = torch.zeros(int(max(int(edge[0].max()) + 1, int(hubs.max()) + 1)), dtype=torch.bool, device=edge.device)
+            in_hub[hubs] = True
+            hub_edge = in_hub[edge[0]]
+            sel_main = (mine & ~hub_edge).nonzero().flatten()
+            he = hub_edge.nonzero().flatten()                               # original order
+            order = torch.sort(edge[0, he], stable=True).indices            # grouped by hub row, original order inside
+            he = he[order]
+            hidx = torch.searchsorted(hubs, edge[0, he])                    # position of the row in hub_ids (ascending)
+            cnt = torch.bincount(hidx, minlength=self.n_ghost)
+            off = torch.cumsum(cnt, 0) - cnt
+            pos = torch.arange(he.numel(), device=edge.device) - off[hidx]
+            take = (pos * self.world) // cnt[hidx].clamp_(min=1) == rank    # contiguous 1/world slice of every hub row
+            he, hidx = he[take], hidx[take]
+            sel1 = torch.cat((sel_main, he))
+            rows = torch.cat((edge[0, sel_main] - lo, (hi - lo) + hidx))
+        else:
+            sel1 = mine.nonzero().flatten()
+            rows = edge[0, sel1] - lo
+        e_loc = torch.stack((rows, self.remap(edge[1, sel1])), dim=0)
         t_loc = edge_type[sel1]
         if nhop is not None and nhop.numel() > 0:
             sel2 = ((nhop[:, 3] >= lo) & (nhop[:, 3] < hi)).nonzero().flatten()
@@ -72,14 +110,39 @@ class _Done:
         return True
 
 
+class GhostRows:
+    """Exchange helpers for the hub rows that are split across ranks (see RowPartition)."""
+
+    def __init__(self, partition, rank, device, group=None):
+        owner, local = partition.hub_owner()
+        self.n = partition.n_ghost
+        self.group = group
+        self.mine = (owner == rank).to(device)                               # [n_ghost] bool: hubs this rank owns
+        self.mine_local = local[owner == rank].to(device)                    # their row index among this rank's rows
+        self.padded_ids = partition.remap(partition.hub_ids).to(device)      # their row in a gathered table
+
+    def gather_rows(self, local_rows):
+        """[n_local, W] -> [n_ghost, W]: the hub rows, from their owners, on every rank."""
+        buf = local_rows.new_zeros(self.n, local_rows.shape[1])
+        buf[self.mine] = local_rows[self.mine_local]
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        return buf
+
+    def sum_partials(self, ghost_rows):
+        """In-place sum over ranks of the [n_ghost, W] partials every rank computed from its edge slice."""
+        dist.all_reduce(ghost_rows, op=dist.ReduceOp.SUM, group=self.group)
+        return ghost_rows
+
+
 class DistContext:
     """Collectives of the partitioned path; attached to a KGraph as `graph.dist`."""
 
-    def __init__(self, partition, rank, group=None):
+    def __init__(self, partition, rank, group=None, device=None):
         self.part = partition
         self.rank = rank
         self.group = group
         self.world = partition.world
+        self.ghost = GhostRows(partition, rank, device, group) if partition.n_ghost else None
 
     @property
     def n_local(self):
@@ -152,7 +215,7 @@ class PartitionedKBGAT:
     the replicated relation / attention parameters, and the CSR / CSC layouts of its own edges."""
 
     def __init__(self, n_ent, n_rel, edge, edge_type, nhop, in_dim, out_dim, nheads, alpha, device,
-                 entity_emb=None, relation_emb=None, seed=0, group=None, state_dict=None):
+                 entity_emb=None, relation_emb=None, seed=0, group=None, state_dict=None, hub_split=0.05):
         from .models import SpKBGATModified
         from .graph import KGraph
         self.rank = dist.get_rank(group)
@@ -161,8 +224,17 @@ class PartitionedKBGAT:
         edge = edge.to(device); edge_type = edge_type.to(device)
         nhop = nhop.to(device) if nhop is not None and nhop.numel() else None
         agg = edge[0] if nhop is None else torch.cat((edge[0], nhop[:, 3]))
-        self.part = RowPartition(balanced_row_bounds(agg, n_ent, self.world))
-        del agg
+        deg = torch.bincount(agg, minlength=n_ent)
+        # rows holding more than hub_split x (edges per rank) are split across the ranks (graphs without 2-hop rows)
+        hub_ids = None
+        if self.world > 1 and hub_split and nhop is None:
+            hub_ids = (deg > int(hub_split * agg.numel() / self.world)).nonzero().flatten()
+            if hub_ids.numel() == 0 or hub_ids.numel() > 1024:
+                hub_ids = None
+            else:
+                deg[hub_ids] = 0
+        self.part = RowPartition(bounds_from_degrees(deg, n_ent, self.world), hub_ids)
+        del agg, deg
         lo, hi = self.part.rows_of(self.rank)
         self.lo, self.hi = lo, hi
         e_loc, t_loc, nh_loc, _, _ = self.part.local_edges(self.rank, edge, edge_type, nhop)
@@ -185,9 +257,10 @@ class PartitionedKBGAT:
         self.model = self.model.to(device)
         self.n_rel = n_rel
         self.group = group
-        self.graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, hi - lo, n_rel, device=device,
-                            n_cols=self.world * self.part.max_rows)
-        self.graph.dist = DistContext(self.part, self.rank, group)
+        self.graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, hi - lo + self.part.n_ghost, n_rel,
+                            device=device, n_cols=self.world * self.part.max_rows)
+        self.graph.dist = DistContext(self.part, self.rank, group, device)
+        self.graph.n_ghost = self.part.n_ghost
         self._local_edges_dev = (e_loc, t_loc, nh_loc)
         self.batch = torch.arange(hi - lo, device=device)
         self.g_ent = None
@@ -211,9 +284,10 @@ class PartitionedKBGAT:
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             e_loc, t_loc, nh_loc = (t.to(self.device, non_blocking=True) for t in host)
-            graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, self.hi - self.lo, self.n_rel,
-                           device=self.device, n_cols=self.world * self.part.max_rows)
+            graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, self.hi - self.lo + self.part.n_ghost,
+                           self.n_rel, device=self.device, n_cols=self.world * self.part.max_rows)
             graph.dist = self.graph.dist
+            graph.n_ghost = self.part.n_ghost
             _, _, loss = self.step(graph)
             res.copy_(loss.detach().reshape(1), non_blocking=True)
             torch.cuda.synchronize()

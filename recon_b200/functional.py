@@ -316,6 +316,34 @@ def seg_gather(ptr, src, pos, hubs, G, ldg, rec, geom, dst, n_seg, tag):
         _lib.current_tag = ""
 
 
+def _ghost_combine(ghost, vals, den, sw, n, H):
+    """Hub rows split across ranks (dist.RowPartition): rows n.. of `vals` [n_ext, H*W] hold this rank's slice result
+    normalised by its own denominator (num_loc / den_loc), `den` / `sw` [n_ext, H] the slice sums. Recovers the
+    un-normalised partials, sums them over the ranks (GAT/layers.py:150-169 is linear in the edges up to the final
+    division) and writes num / den and den back; sw keeps the LOCAL slice sum (the backward wants the partial)."""
+    ng = ghost.n
+    W = vals.shape[1] // H
+    v = vals[n:].view(ng, H, W)
+    d = den[n:]
+    d0 = torch.where(sw[n:] == 0, torch.zeros_like(d), d)           # an empty slice reports den = 1e-12 (layers.py:152)
+    buf = torch.cat(((v * d0.unsqueeze(-1)).reshape(ng, H * W), d0), dim=1)
+    ghost.sum_partials(buf)
+    dg = buf[:, H * W:]
+    dg = torch.where(dg == 0, torch.full_like(dg, 1e-12), dg)
+    vals[n:] = (buf[:, :H * W].view(ng, H, W) / dg.unsqueeze(-1)).reshape(ng, H * W)
+    den[n:] = dg
+
+
+def _ghost_dout(ghost, dout, n, n_ext):
+    """[n, W] gradient of this rank's rows -> [n_ext, W]: ghost rows get the owners' gradient rows (on every rank), the
+    owner's own (edge-less) copy of a hub row gets zero: its gradient flows through the ghost row."""
+    ext = torch.empty(n_ext, dout.shape[1], dtype=dout.dtype, device=dout.device)
+    ext[:n] = dout
+    ext[n:] = ghost.gather_rows(dout)
+    ext[ghost.mine_local] = 0
+    return ext
+
+
 class AttentionGroupFn(torch.autograd.Function):
     """One fused group of <=4 heads: (X, Wn, Rel, Wr) -> ELU?(attention output) [N, H*D].
 
@@ -330,6 +358,7 @@ class AttentionGroupFn(torch.autograd.Function):
     def forward(ctx, X, Wn, Rel, Wr, graph, geom, alpha, apply_elu, mask_csr, nanflag):
         X = tc_friendly(X.contiguous()); Wn = Wn.contiguous(); Rel = Rel.contiguous(); Wr = Wr.contiguous()
         dist = getattr(graph, "dist", None)
+        ghost = dist.ghost if dist is not None else None
         Wd = geom.Wd
         mode = "local"
         X_all = None
@@ -355,14 +384,34 @@ class AttentionGroupFn(torch.autograd.Function):
             P2, mine = dist.gather_buffer(Wd, X.device)
             gemm_nn(X, Wn[:, Wd:], out=mine)
             h = dist.all_gather_start(P2)       # in flight while P1~ and P3~ are projected
-            P1 = gemm_nn(X, Wn[:, :Wd])
+            n = X.shape[0]
+            if ghost is None:
+                P1 = gemm_nn(X, Wn[:, :Wd])
+            else:                               # + the P1~ rows of the hub rows whose edges are split across ranks
+                P1 = torch.empty(n + ghost.n, Wd, dtype=torch.float32, device=X.device)
+                gemm_nn(X, Wn[:, :Wd], out=P1[:n])
+                gemm_nn(tc_friendly(ghost.gather_rows(X)), Wn[:, :Wd], out=P1[n:])
             P3 = gemm_nn(Rel, Wr)
             h.wait()
-        out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
+        if ghost is not None and mode != "proj":
+            raise NotImplementedError("hub rows split across ranks need the projected exchange (or the aggregate-then-project path)")
+        if ghost is None:
+            out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag)
+            out_ret = out
+        else:
+            n = X.shape[0]
+            out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, False, mask_csr, nanflag)
+            _ghost_combine(ghost, out, den, sw, n, geom.H)
+            nanflag.add_(torch.isnan(out[n:]).any().to(torch.int32))
+            if apply_elu:
+                _lib.check(_lib.load().spk_elu_inplace(_lib.ptr(out), out.stride(0), out.shape[0], out.shape[1],
+                                                       _lib.stream_ptr()), "elu_inplace")
+            out[ghost.mine_local] = out[n:][ghost.mine]          # the owner's copy of a hub row takes the combined result
+            out_ret = out[:n]
         ctx.save_for_backward(X, Wn, Rel, Wr, P1, P2, P3, out, den, sw, X_all if X_all is not None else X.new_empty(0))
         ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr, ctx.mode = graph, geom, alpha, apply_elu, mask_csr, mode
         ctx.mark_non_differentiable(den, sw)
-        return out, den, sw
+        return out_ret, den, sw
 
     @staticmethod
     def backward(ctx, dout, _dden, _dsw):
@@ -391,7 +440,11 @@ class AttentionGroupFn(torch.autograd.Function):
             # The reduce-scatter starts right after the column pass and runs under the relation pass and the products
             # that only need dP1~.
             mr = dist.part.max_rows
-            dP1 = torch.empty(n, Wd, dtype=torch.float32, device=dev)
+            ghost = dist.ghost
+            n_ext = n + (ghost.n if ghost is not None else 0)
+            if ghost is not None:
+                dout = _ghost_dout(ghost, dout, n, n_ext)
+            dP1 = torch.empty(n_ext, Wd, dtype=torch.float32, device=dev)
             dP2_all = torch.empty_like(P2)
             colsum = torch.empty(P2.shape[0], geom.H, dtype=torch.float32, device=dev)
             pend = {}
@@ -410,6 +463,10 @@ class AttentionGroupFn(torch.autograd.Function):
                 else:
                     start_main()
                 h3 = dist.all_reduce_start(dP3)
+                if ghost is not None:           # dP1~ of a hub row = sum of the ranks' partials -> its owner's row
+                    gsum = ghost.sum_partials(dP1[n:].contiguous())
+                    dP1[ghost.mine_local] = gsum[ghost.mine]
+                    dP1 = dP1[:n]
                 if need_x:
                     dX = gemm_nn(dP1, WnT[:Wd])
                 if need_w:
@@ -531,8 +588,10 @@ class AggGroupFn(torch.autograd.Function):
         lib = _lib.load()
         X = X.contiguous(); Rel = Rel.contiguous(); Wa = Wa.contiguous(); V = V.contiguous(); V3 = V3.contiguous()
         n, dev = graph.n_nodes, X.device
+        n_loc = X.shape[0]
         H, D, LZ = geom.H, geom.D, geom.LZ
         dist = getattr(graph, "dist", None)
+        ghost = dist.ghost if dist is not None else None
         # multi-GPU: rows are partitioned, the gathered table must cover all nodes -> all-gather the
         # X~ rows (LX = 56 floats for F = 50: 3.7x fewer bytes than the projected rows). The table builder writes this
         # rank's rows straight into the exchange buffer; the all-gather runs in place, under the Rel~ table build.
@@ -546,6 +605,13 @@ class AggGroupFn(torch.autograd.Function):
             hx = dist.all_gather_start(Xc)
             Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
             hx.wait()
+            if ghost is not None:
+                # hub rows split across ranks: their X~ rows arrived with the all-gather; park copies right after this
+                # rank's own rows (spare rows of its slot: RowPartition.max_rows reserves them) so that the row table
+                # [own rows | ghost rows] is one contiguous view of the exchange buffer
+                lo = dist.rank * dist.part.max_rows
+                Xc[lo + n_loc:lo + n] = Xc[ghost.padded_ids]
+                Xt = Xc[lo:lo + n]
         Z = torch.empty(n, H * LZ, dtype=torch.float32, device=dev)
         den = torch.empty(n, H, dtype=torch.float32, device=dev)
         sw = torch.empty(n, H, dtype=torch.float32, device=dev)
@@ -561,12 +627,17 @@ class AggGroupFn(torch.autograd.Function):
         partial = _hub_partial(graph.row_hubs, 264, dev)
         graph.row_hubs.fill(a.hub, partial, 264)
         _lib.check(lib.spk_agg_fwd(C.byref(a), _lib.stream_ptr()), "agg_fwd")
+        if ghost is not None:                               # Zn of a hub row: partial sums of every rank's edge slice
+            _ghost_combine(ghost, Z, den, sw, n_loc, H)
         out = torch.empty(n, H * D, dtype=torch.float32, device=dev)
         for h in range(H):                                  # a.mm(.) of layers.py:137 on the aggregated rows (+ ELU 175)
             gemm_nn(Z[:, h * LZ:(h + 1) * LZ], Wa[h], out=out[:, h * D:(h + 1) * D], act=int(apply_elu))
+        if ghost is not None:
+            nanflag.add_(torch.isnan(out[n_loc:]).any().to(torch.int32))
+            out[ghost.mine_local] = out[n_loc:][ghost.mine]  # the owner's copy of a hub row takes the combined result
         ctx.save_for_backward(X, Rel, Wa, V, V3, Xt, Rt, Z, out, den, sw, Xc)
         ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr = graph, geom, alpha, apply_elu, mask_csr
-        return out
+        return out[:n_loc] if ghost is not None else out
 
     @staticmethod
     def backward(ctx, dout):
@@ -576,9 +647,13 @@ class AggGroupFn(torch.autograd.Function):
         dist = getattr(graph, "dist", None)
         graph.build_backward()
         n, dev = graph.n_nodes, X.device
+        n_loc = X.shape[0]
+        ghost = dist.ghost if dist is not None else None
         H, D, LZ, Fp, Rp = geom.H, geom.D, geom.LZ, geom.Fp, geom.Rp
         f32 = dict(dtype=torch.float32, device=dev)
         dout = dout.contiguous()
+        if ghost is not None:                               # + the owners' gradient rows of the split hub rows
+            dout = _ghost_dout(ghost, dout, n_loc, n)
         dhn = torch.empty(n, H * D, **f32)
         dden = torch.empty(n, H, **f32)
         _lib.check(lib.spk_agg_bwd_pre(_lib.ptr(out), _lib.ptr(dout), out.stride(0), _lib.ptr(den), H, D,
@@ -589,7 +664,12 @@ class AggGroupFn(torch.autograd.Function):
         for h in range(H):
             dh = dhn[:, h * D:(h + 1) * D]
             gemm_nn(dh, Wa[h].t().contiguous(), out=dZ[:, h * LZ:(h + 1) * LZ])
-            gemm_tn(Z[:, h * LZ:(h + 1) * LZ], dh, out=dWa[h])
+            if ghost is None:
+                gemm_tn(Z[:, h * LZ:(h + 1) * LZ], dh, out=dWa[h])
+            else:                                           # ghost rows are replicated: only their owner counts them
+                gemm_tn(Z[:n_loc, h * LZ:(h + 1) * LZ], dh[:n_loc], out=dWa[h])
+                gemm_tn((Z[n_loc:, h * LZ:(h + 1) * LZ] * ghost.mine.unsqueeze(1)).contiguous(), dh[n_loc:], out=dWa[h],
+                        accumulate=True)
         Gx = torch.empty(n, H * Fp, **f32)
         Gr = torch.empty(n, H * Rp, **f32)
         rowout = torch.empty(n, Fp + 4, **f32)
@@ -626,15 +706,19 @@ class AggGroupFn(torch.autograd.Function):
         if dist is not None:
             dist.all_reduce(dRc)
             dist.all_reduce(dWa)
+            if ghost is not None:                         # row-side gradient of a hub row = sum of the ranks' partials
+                gsum = ghost.sum_partials(rowout[n_loc:].contiguous())
+                rowout[ghost.mine_local] = gsum[ghost.mine]
             hx.wait()
-            dXc = dXc_pad[:n]
+            dXc = dXc_pad[:n_loc]
             del dXc_all
+        n = n_loc
         dX = torch.empty(n, geom.F, **f32)
         dq = torch.empty(n, 4, **f32)
         _lib.check(lib.spk_agg_dx(_lib.ptr(rowout), rowout.stride(0), _lib.ptr(dXc), dXc.stride(0), _lib.ptr(V), n,
                                   geom.F, geom.Fx4, H, _lib.ptr(dX), dX.stride(0), _lib.ptr(dq), _lib.stream_ptr()),
                    "agg_dx")
-        dV = gemm_tn(Xt[:, :geom.F], dq) if ctx.needs_input_grad[3] else None      # Xt rows start with x (16 B aligned stride)
+        dV = gemm_tn(Xt[:n, :geom.F], dq) if ctx.needs_input_grad[3] else None     # Xt rows start with x (16 B aligned stride)
         if dV is not None and dist is not None:
             dist.all_reduce(dV)
         dq3 = dRc[:, H * Rp:H * Rp + H].contiguous()                      # [R, H]
@@ -656,8 +740,9 @@ def attention_group(X, Rel, a_list, a2_list, graph, alpha, apply_elu, mask_csr, 
     outs = []
     # the C ABI takes raw pointers without row counts: check here what the reference's indexing would have caught
     # (IndexError from x[edge[..]] / relation_embed[edge_type], GAT/layers.py:129, models.py:156)
-    if X.shape[0] != graph.n_nodes:
-        raise IndexError(f"entity table has {X.shape[0]} rows but the graph was built for {graph.n_nodes} nodes")
+    if X.shape[0] != graph.n_nodes - getattr(graph, "n_ghost", 0):
+        raise IndexError(f"entity table has {X.shape[0]} rows but the graph was built for "
+                         f"{graph.n_nodes - getattr(graph, 'n_ghost', 0)} nodes")
     if getattr(graph, "dist", None) is None and graph.n_cols > X.shape[0]:
         raise IndexError(f"graph gathers from {graph.n_cols} nodes but the entity table has {X.shape[0]} rows")
     if Rel.shape[0] < graph.n_rel:
