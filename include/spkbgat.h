@@ -327,6 +327,54 @@ int spk_corrupt_triples(const int64_t* positives, int64_t n_pos, int32_t ratio, 
                         int64_t n_ent, int64_t n_rel, const int64_t* init_entities, const int64_t* init_relations,
                         uint64_t seed, int64_t* out_indices, float* out_values, spk_stream_t stream);
 
+/* ---- K0b (SURVEY.md 8 a-1, 8b "spk_nhop_build"): batch adjacency + 2-hop path rows of a batch of source entities, bit-exact
+ * (values and order) with Corpus.get_batch_adj_data / bfs / get_batch_nhop_neighbors_all (GAT/create_batch.py:391-436,
+ * 788-895). The triple graph is the distinct-neighbour adjacency in the reference's insertion order (int32 device arrays):
+ *   uptr [n_nodes+1]  first pair of every head         ut  [n_pairs]  tail of the pair (first-seen order per head)
+ *   ur0  [n_pairs]    first relation of the pair       ugs / uge [n_pairs]  range of its parallel relations in rs
+ *   rs   [n_triples]  relation ids grouped by (head, tail), file order inside a group
+ * Sizes are data dependent: every buffer (scratch and results) is obtained from `alloc` (the caller's allocator, e.g.
+ * PyTorch's; must return 16-byte aligned device memory that stays valid until the caller releases it); the call
+ * synchronises the stream to read the sizes back. Results: adj_idx int64 [2, e1] = [trgts; srcs], adj_val int64 [e1],
+ * nhop int32 [e2, 4] rows [s, r(s->m)[0], r(m->t)[0], t]. flags: bit 0 = partial_2hop (create_batch.py:883-884: the first
+ * path of every source only), bit 1 = adjacency only (no 2-hop rows). */
+typedef void* (*spk_alloc_fn)(void* ctx, int64_t bytes);
+typedef struct {
+    const int32_t* uptr; const int32_t* ut; const int32_t* ur0; const int32_t* ugs; const int32_t* uge; const int32_t* rs;
+    int32_t n_nodes; int32_t n_pairs; int32_t n_triples; int32_t reserved;
+} spk_triple_graph;
+typedef struct {
+    int64_t* adj_idx; int64_t* adj_val; int32_t* nhop;
+    int64_t e1; int64_t e2;
+} spk_nhop_result;
+int spk_nhop_build(const spk_triple_graph* graph, const int64_t* sources, int64_t n_sources, int32_t flags,
+                   spk_alloc_fn alloc, void* alloc_ctx, spk_nhop_result* result, spk_stream_t stream);
+
+/* ---- N4: ConvKB scoring of the hot path's output embeddings ----
+ * Reference: ConvKB.forward GAT/layers.py:31-48 (live path fc2(LeakyReLU(fc1([h|r|t])))), SpKBGATConvOnly.forward /
+ * batch_test GAT/models.py:294-304, tanh(e . W_ent2rel[r]) GAT_sep_space/models.py:316-320, the all-relations ranking of
+ * GAT/create_batch.py:1367-1393. The dense products go through spk_gemm_nn_tc / spk_gemm_tn_tc.
+ * spk_gather_concat: out[b, p*D:(p+1)*D] = src[p][row, :D], row = idx[p] ? idx[p][b*stride[p]] : b, for p < n_pieces <= 3
+ *                    (the [h|r|t] concatenation from an int64 [B,3] triple tensor: idx = triples+p, stride = 3);
+ *                    an index outside [0, rows[p]) sets *err_flag (and reads row 0).
+ * spk_mlp_head_fwd:  out[b] = b2 + sum_d w2[d] * lrelu(H1[b,d] + b1[d])            (fc1 bias + LeakyReLU + fc2)
+ * spk_mlp_head_bwd:  dH1[b,d] = dout[b] * w2[d] * lrelu'(pre), act[b,d] = lrelu(pre)
+ * spk_tanh_fwd / _bwd: x = tanh(x) in place;  dpre = dout * (1 - y^2)
+ * spk_rank_scores:   out[i,r] = b2 + sum_d w2[d] * lrelu(U[i,d] + Bt[r,d]), the re-associated fc1: U = A[h] + C[t] + b1 per
+ *                    test pair, Bt = Rel . W1b^T per relation; D <= 512. */
+int spk_gather_concat(const float* const* src, const int64_t* ld, const int64_t* const* idx, const int64_t* stride,
+                      const int64_t* rows, int32_t n_pieces, int64_t n_out, int32_t D, float* out, int64_t ldo,
+                      int32_t* err_flag, spk_stream_t stream);
+int spk_mlp_head_fwd(const float* H1, int64_t ldh, const float* b1, const float* w2, const float* b2, float slope,
+                     int64_t n_rows, int32_t D, float* out, spk_stream_t stream);
+int spk_mlp_head_bwd(const float* H1, int64_t ldh, const float* b1, const float* w2, float slope, const float* dout,
+                     int64_t n_rows, int32_t D, float* dH1, int64_t ldd, float* act, int64_t lda, spk_stream_t stream);
+int spk_tanh_fwd(float* x, int64_t ld, int64_t n_rows, int32_t width, spk_stream_t stream);
+int spk_tanh_bwd(const float* y, int64_t ldy, const float* dout, int64_t ldo, int64_t n_rows, int32_t width, float* dpre,
+                 int64_t ldp, spk_stream_t stream);
+int spk_rank_scores(const float* U, int64_t ldu, const float* Bt, int64_t ldb, const float* w2, const float* b2, float slope,
+                    int64_t n_pairs, int32_t n_rel, int32_t D, float* out, int64_t ldo, spk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,19 @@ class AggBwdArgs(C.Structure):
 
 _VP, _I64, _I32 = C.c_void_p, C.c_int64, C.c_int32
 
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int64)
+
+
+class TripleGraphArgs(C.Structure):
+    _fields_ = [("uptr", C.c_void_p), ("ut", C.c_void_p), ("ur0", C.c_void_p), ("ugs", C.c_void_p), ("uge", C.c_void_p),
+                ("rs", C.c_void_p), ("n_nodes", C.c_int32), ("n_pairs", C.c_int32), ("n_triples", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class NhopResult(C.Structure):
+    _fields_ = [("adj_idx", C.c_void_p), ("adj_val", C.c_void_p), ("nhop", C.c_void_p), ("e1", C.c_int64), ("e2", C.c_int64)]
+
+
 class LossBwdArgs(C.Structure):
     _fields_ = [("segptr", C.c_void_p), ("inc", C.c_void_p), ("coef", C.c_void_p), ("sgn", C.c_void_p),
                 ("gscale", C.c_void_p), ("out", C.c_void_p), ("ldo", C.c_int64),
@@ -176,6 +189,13 @@ SIGNATURES = {
     "spk_sgd_step": (_I32, [C.POINTER(SgdArgs), _VP]),
     "spk_triple_keys": (_I32, [_VP, _I64, _I64, _I64, _VP, _VP, _VP]),
     "spk_corrupt_triples": (_I32, [_VP, _I64, _I32, _VP, _I64, _I64, _I64, _VP, _VP, C.c_uint64, _VP, _VP, _VP]),
+    "spk_nhop_build": (_I32, [C.POINTER(TripleGraphArgs), _VP, _I64, _I32, ALLOC_FN, _VP, C.POINTER(NhopResult), _VP]),
+    "spk_gather_concat": (_I32, [_VP, _VP, _VP, _VP, _VP, _I32, _I64, _I32, _VP, _I64, _VP, _VP]),
+    "spk_mlp_head_fwd": (_I32, [_VP, _I64, _VP, _VP, _VP, C.c_float, _I64, _I32, _VP, _VP]),
+    "spk_mlp_head_bwd": (_I32, [_VP, _I64, _VP, _VP, C.c_float, _VP, _I64, _I32, _VP, _I64, _VP, _I64, _VP]),
+    "spk_tanh_fwd": (_I32, [_VP, _I64, _I64, _I32, _VP]),
+    "spk_tanh_bwd": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _VP, _I64, _VP]),
+    "spk_rank_scores": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, C.c_float, _I64, _I32, _I32, _VP, _I64, _VP]),
     "spk_export_json": (_I32, [_VP, _I64, _I64, _I64, C.c_char_p, _I32]),
     "spk_export_bin": (_I32, [_VP, _I64, _I64, _I64, C.c_char_p]),
     "spk_import_json_shape": (_I32, [C.c_char_p, C.POINTER(_I64), C.POINTER(_I64)]),

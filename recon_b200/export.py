@@ -133,3 +133,14 @@ def save_entity_relation_final_embeddings(model_gat, output_folder, binary_sidec
                binary_sidecar=binary_sidecar)
     save_embed(model_gat.final_relation_embeddings, os.path.join(output_folder, "final_relation_embeddings.json"),
                binary_sidecar=binary_sidecar)
+    if getattr(model_gat, "W_ent2rel", None) is not None:                  # GAT_sep_space/main.py:982
+        save_ent2rel(model_gat, output_folder)
+
+
+def save_ent2rel(model_gat, output_folder):
+    """GAT_sep_space/main.py:982: np.save(join(folder, 'W_ent2rel.json'), W_ent2rel) -- numpy appends the suffix, so the file
+    is `W_ent2rel.json.npy` ([R, H*D, H*D] fp32, the relation-space projection the sep-space consumer loads)."""
+    import numpy as np
+    path = os.path.join(output_folder, "W_ent2rel.json")
+    np.save(path, np.array(model_gat.W_ent2rel.detach().cpu()))
+    return path + ".npy"

@@ -3,7 +3,7 @@ parameter names and shapes), running on libspkbgat's sm_100a kernels. No CPU pat
 
   SpecialSpmmFunctionFinal / SpecialSpmmFinal  <- GAT/layers.py:51-84
   SpGraphAttentionLayer                        <- GAT/layers.py:87-181
-  ConvKB                                       <- GAT/layers.py:12-48 (downstream scorer, kept for import compatibility)
+  ConvKB                                       <- GAT/layers.py:12-48 (lives in recon_b200/convkb.py; re-exported here)
 """
 import torch
 import torch.nn as nn
@@ -133,21 +133,10 @@ class SpGraphAttentionLayer(nn.Module):
         return self.__class__.__name__ + ' (' + str(self.in_features) + ' -> ' + str(self.out_features) + ')'
 
 
-class ConvKB(nn.Module):
-    """Downstream triple scorer of the reference (GAT/layers.py:12-48): two-layer MLP over [h|r|t].
-    Not part of the accelerated path; provided so `from layers import SpGraphAttentionLayer, ConvKB` keeps working."""
-
-    def __init__(self, input_dim, input_seq_len, in_channels, out_channels, drop_prob, alpha_leaky):
-        super().__init__()
-        self.conv_layer = nn.Conv2d(in_channels, out_channels, (1, input_seq_len))
-        self.dropout = nn.Dropout(drop_prob)
-        self.non_linearity = nn.LeakyReLU()
-        self.fc_layer = nn.Linear(input_dim * out_channels, 1)
-        self.fc1 = nn.Linear(input_dim * 3, input_dim)
-        self.nl1 = nn.LeakyReLU()
-        self.fc2 = nn.Linear(input_dim, 1)
-        nn.init.xavier_uniform_(self.fc_layer.weight, gain=1.414)
-        nn.init.xavier_uniform_(self.conv_layer.weight, gain=1.414)
-
-    def forward(self, conv_input):
-        return self.fc2(self.nl1(self.fc1(conv_input)))
+def __getattr__(name):
+    """`from layers import SpGraphAttentionLayer, ConvKB` (GAT/models.py:6) keeps working: ConvKB lives in convkb.py
+    (imported lazily: that module imports this one)."""
+    if name == "ConvKB":
+        from .convkb import ConvKB
+        return ConvKB
+    raise AttributeError(name)

@@ -97,7 +97,10 @@ class SpGAT(nn.Module):
 
 class SpKBGATModified(nn.Module):
     def __init__(self, initial_entity_emb, initial_relation_emb, entity_out_dim, relation_out_dim,
-                 drop_GAT, alpha, nheads_GAT, initial_entity_emb_params=None):
+                 drop_GAT, alpha, nheads_GAT, initial_entity_emb_params=None, *, sep_space=False):
+        """`sep_space=True` adds the GAT_sep_space variant's relation-space projection parameter W_ent2rel
+        [R, H*D, H*D] (GAT_sep_space/models.py:136-140), used by SpKBGATConvOnly(..., model_gat) and saved / loaded
+        with the state dict; loading a checkpoint that carries the key creates it as well."""
         super().__init__()
         self.num_nodes = initial_entity_emb.shape[0]
         self.entity_in_dim = initial_entity_emb.shape[1]
@@ -119,8 +122,24 @@ class SpKBGATModified(nn.Module):
                                   self.drop_GAT, self.alpha, self.nheads_GAT_1)
         self.W_entities = nn.Parameter(torch.zeros(size=(self.entity_in_dim, hd)))
         nn.init.xavier_uniform_(self.W_entities.data, gain=1.414)
+        self.nonlinearity_ent2rel = torch.tanh
+        if sep_space:
+            self.W_ent2rel = nn.Parameter(torch.zeros(size=(self.num_relation, hd, hd)))
+            nn.init.xavier_uniform_(self.W_ent2rel.data, gain=1.414)
         self._graph_cache = {}
         self.graph_cache = True
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """trained_*.pth of either reference variant loads: a GAT_sep_space checkpoint brings W_ent2rel into a model built
+        without it, and a GAT checkpoint leaves an existing W_ent2rel at its initial value."""
+        has = "W_ent2rel" in self._parameters
+        if "W_ent2rel" in state_dict and not has:
+            w = state_dict["W_ent2rel"]
+            self.W_ent2rel = nn.Parameter(torch.empty_like(w, device=self.W_entities.device))
+        elif has and "W_ent2rel" not in state_dict:
+            state_dict = dict(state_dict)
+            state_dict["W_ent2rel"] = self.W_ent2rel.detach()
+        return super().load_state_dict(state_dict, strict=strict, **kw)
 
     # -- graph handling ------------------------------------------------------------------------
     def prepare_graph(self, adj, train_indices_nhop=None):

@@ -6,6 +6,10 @@ with the reference's Python dict / queue code:
   Corpus.get_batch_adj_data           GAT/create_batch.py:391-436  -> ([trgts; srcs], vals)
   Corpus.get_batch_nhop_neighbors_all GAT/create_batch.py:871-895  -> rows [s, r(s->m)[0], r(m->t)[0], t]
 
+`TripleGraph.batch_edges` runs entirely in libspkbgat (spk_nhop_build, csrc/spk_nhop.cu: prefix sums, level expansion,
+stable radix sorts, compaction; buffers come from PyTorch's allocator through a callback). Only the once-per-graph
+construction of the distinct-neighbour adjacency below still uses torch for index glue around the library's sorts.
+
 Instead of a per-source BFS the whole batch is expanded at once and the BFS tie-breaks are recovered by
 STABLE sorts (libspkbgat's radix sort, graph.sort_pairs):
   * first-occurrence order of the distinct out-neighbours of every head = stable sort of the (head, tail)
@@ -13,10 +17,12 @@ STABLE sorts (libspkbgat's radix sort, graph.sort_pairs):
   * a 2-hop target t of source s is kept iff it is not s, not a 1-hop neighbour of s, and this is the first
     candidate (in (mid, tail) discovery order) reaching t: sort the records (blockers first, then candidates in
     discovery order) stably by (s, t) and keep group heads that are candidates.
-torch is used for allocation and index glue (cumsum / repeat_interleave / comparisons on int tensors).
 """
+import ctypes as C
+
 import torch
 
+from . import _lib
 from .graph import sort_pairs, _key_bits
 
 
@@ -65,9 +71,46 @@ class TripleGraph:
         self.ur0 = self.rs[gstart][q]                            # first relation of the pair: graph[h][t][0]
         self.ugs, self.uge = gstart[q], gend[q]                  # its parallel relations: rs[ugs:uge]
         self.uptr = torch.searchsorted(self.uh, torch.arange(self.n_nodes + 1, device=device))
+        self._i32 = None
 
     def batch_edges(self, batch_sources, partial_2hop=False, want_nhop=True):
-        """Returns (adj_indices int64[2,E1], adj_values int64[E1], nhop int32[E2,4]) for the given ordered sources."""
+        """Returns (adj_indices int64[2,E1], adj_values int64[E1], nhop int32[E2,4]) for the given ordered sources
+        (one spk_nhop_build call; every kernel of it is libspkbgat's)."""
+        lib = _lib.load()
+        dev = self.device
+        s = torch.as_tensor(batch_sources, dtype=torch.int64, device=dev).contiguous()
+        if self._i32 is None:
+            self._i32 = tuple(t.to(torch.int32).contiguous() for t in (self.uptr, self.ut, self.ur0, self.ugs, self.uge, self.rs))
+        g = _lib.TripleGraphArgs()
+        g.uptr, g.ut, g.ur0, g.ugs, g.uge, g.rs = (t.data_ptr() for t in self._i32)
+        g.n_nodes, g.n_pairs, g.n_triples = self.n_nodes, self.ut.numel(), self.rs.numel()
+        bufs = {}
+
+        def alloc(_ctx, nbytes):
+            try:
+                t = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+            except RuntimeError:                              # out of memory: the C side reports it
+                return None
+            bufs[t.data_ptr()] = t
+            return t.data_ptr()
+
+        res = _lib.NhopResult()
+        with torch.cuda.device(dev):
+            rc = lib.spk_nhop_build(C.byref(g), s.data_ptr() if s.numel() else None, s.numel(),
+                                    (1 if partial_2hop else 0) | (0 if want_nhop else 2), _lib.ALLOC_FN(alloc), None,
+                                    C.byref(res), _lib.stream_ptr())
+        if rc == 5:
+            raise IndexError("batch source id out of range")
+        _lib.check(rc, "nhop_build")
+        e1, e2 = int(res.e1), int(res.e2)
+        adj_idx = bufs[res.adj_idx].view(torch.int64)[:2 * e1].view(2, e1)
+        adj_val = bufs[res.adj_val].view(torch.int64)[:e1]
+        nhop = bufs[res.nhop].view(torch.int32)[:4 * e2].view(e2, 4) if res.nhop else torch.zeros((0, 4), dtype=torch.int32, device=dev)
+        return adj_idx, adj_val, nhop
+
+    def batch_edges_torch(self, batch_sources, partial_2hop=False, want_nhop=True):
+        """The same construction written with torch index ops on top of the library's sorts (round-1 form); kept as an
+        independent cross-check of spk_nhop_build for the tests, not used by the product."""
         dev = self.device
         s = torch.as_tensor(batch_sources, dtype=torch.int64, device=dev)
         nb = s.numel()

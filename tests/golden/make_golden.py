@@ -287,9 +287,87 @@ def loss_case(name, n_ent, n_rel, width, n_pos, ratio, margin, seed, hub_share=0
     print(name, "ok", float(out["f32.loss"]), tuple(tri.shape))
 
 
+def _load_sep_space():
+    """GAT_sep_space/{layers,models}.py under private module names (they shadow the GAT/ module names)."""
+    import importlib.util
+    mods = {}
+    for name in ("layers", "models"):
+        spec = importlib.util.spec_from_file_location("_sep_" + name, f"/root/reference/GAT_sep_space/{name}.py")
+        mod = importlib.util.module_from_spec(spec)
+        saved = sys.modules.get("layers")
+        if name == "models":
+            sys.modules["layers"] = mods["layers"]
+        try:
+            spec.loader.exec_module(mod)
+        finally:
+            if saved is not None:
+                sys.modules["layers"] = saved
+        mod.CUDA = False
+        mods[name] = mod
+    return mods["layers"], mods["models"]
+
+
+def convkb_case(name, n, r, d_half, nheads, batch, n_test, seed, sep_space=False):
+    """SpKBGATConvOnly of the reference (GAT/models.py:242-304, or the GAT_sep_space variant with W_ent2rel,
+    GAT_sep_space/models.py:311-339): forward on a batch of triples, SoftMarginLoss backward (GAT/main.py:753,818-835),
+    batch_test scores of every test triple under every relation (create_batch.py:1367-1393)."""
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    d = d_half * nheads
+    ent0 = torch.randn(n, 10); rel0 = torch.randn(r, 10)
+    mods = _load_sep_space()[1] if sep_space else ref_models
+    conv = mods.SpKBGATConvOnly(ent0, rel0, [d_half, 2 * d_half], [d_half, 2 * d_half], 0.0, 0.0, 0.2, 0.2, [nheads, nheads], 50)
+    conv.final_entity_embeddings.data = torch.nn.functional.normalize(torch.randn(n, d, generator=gen), dim=1)
+    conv.final_relation_embeddings.data = torch.randn(r, d, generator=gen)
+    gat = None
+    if sep_space:
+        gat = types.SimpleNamespace(W_ent2rel=torch.nn.Parameter(torch.randn(r, d, d, generator=gen) * 0.1),
+                                    nonlinearity_ent2rel=torch.tanh)
+    tri = torch.stack((torch.randint(0, n, (batch,), generator=gen), torch.randint(0, r, (batch,), generator=gen),
+                       torch.randint(0, n, (batch,), generator=gen)), dim=1)
+    target = (torch.rand(batch, generator=gen) < 0.3).float() * 2 - 1
+    out = {"triples": tri, "target": target}
+    for k, v in conv.state_dict().items():
+        out["param." + k] = v.detach().clone()
+    if sep_space:
+        out["W_ent2rel"] = gat.W_ent2rel.detach().clone()
+    for tag, m in (("f32", conv), ("f64", copy.deepcopy(conv).double())):
+        g = gat
+        if sep_space and tag == "f64":
+            g = types.SimpleNamespace(W_ent2rel=torch.nn.Parameter(gat.W_ent2rel.detach().double()), nonlinearity_ent2rel=torch.tanh)
+        m.zero_grad()
+        preds = m(None, None, tri, g) if sep_space else m(None, None, tri)
+        loss = torch.nn.SoftMarginLoss()(preds.view(-1), target.to(preds.dtype))
+        loss.backward()
+        out[tag + ".preds"] = preds.detach()
+        out[tag + ".loss"] = loss.detach()
+        for k, prm in m.named_parameters():
+            if prm.grad is not None:
+                out[tag + ".grad." + k] = prm.grad.detach().clone()
+        if sep_space:
+            out[tag + ".grad.W_ent2rel"] = g.W_ent2rel.grad.detach().clone()
+        test = torch.stack((torch.randint(0, n, (n_test,), generator=torch.Generator().manual_seed(seed + 2)),
+                            torch.randint(0, r, (n_test,), generator=torch.Generator().manual_seed(seed + 3)),
+                            torch.randint(0, n, (n_test,), generator=torch.Generator().manual_seed(seed + 4))), dim=1)
+        test[1] = test[0]; test[1, 1] = (test[0, 1] + 1) % r            # an entity pair with two actual relations
+        tb = test.unsqueeze(1).repeat(1, r, 1)
+        tb[:, :, 1] = torch.arange(r).unsqueeze(0)
+        with torch.no_grad():
+            sc = m.batch_test(tb.reshape(-1, 3), g) if sep_space else m.batch_test(tb.reshape(-1, 3))
+        out["test_triples"] = test
+        out[tag + ".scores"] = sc.view(n_test, r)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **{k: np.asarray(v.detach() if isinstance(v, torch.Tensor) else v) for k, v in out.items()})
+    print(name, "ok", float(out["f32.loss"]), tuple(out["f32.scores"].shape))
+
+
 if __name__ == "__main__":
     import warnings
     warnings.filterwarnings("ignore")
+    if len(sys.argv) > 1 and sys.argv[1] == "convkb":
+        convkb_case("convkb_gat", 300, 11, 100, 2, 257, 40, 80)
+        convkb_case("convkb_small", 40, 5, 6, 2, 33, 12, 81)
+        convkb_case("convkb_sep", 120, 7, 20, 2, 129, 25, 82, sep_space=True)
+        sys.exit(0)
     model_case("model_small_uniform", 60, 300, 7, 12, 8, 2, None, 0, [3, 5, 5, 17, 40, 41], 0.0, 0)
     model_case("model_small_zipf_nhop", 80, 400, 9, 12, 8, 2, 1.1, 150, list(range(80)), 0.0, 1)
     model_case("model_small_dropmask", 70, 350, 5, 16, 12, 2, 1.5, 120, list(range(0, 70, 2)), 0.3, 2)

@@ -414,10 +414,55 @@ def test_batch_edges_vs_oracle_random_medium():
     batch = torch.randperm(n, generator=gen)[:150].tolist() + [5, 5]       # duplicates allowed
     want_idx, want_val = OE.batch_adj(graph, batch)
     want_nhop = OE.batch_nhop(graph, batch)
-    idx, val, nhop = TripleGraph(tr, n, device=dev()).batch_edges(batch)
+    tg = TripleGraph(tr, n, device=dev())
+    idx, val, nhop = tg.batch_edges(batch)
     assert idx.cpu().tolist() == want_idx and val.cpu().tolist() == want_val
     assert nhop.cpu().tolist() == want_nhop
+    # spk_nhop_build against the independent torch-glue construction, incl. partial_2hop / adjacency-only / empty batches
+    for kw in (dict(), dict(partial_2hop=True), dict(want_nhop=False)):
+        a = tg.batch_edges(batch, **kw); b = tg.batch_edges_torch(batch, **kw)
+        assert all(torch.equal(x.long(), y.long()) for x, y in zip(a, b)), kw
+    e_idx, e_val, e_nhop = tg.batch_edges([])
+    assert e_idx.shape == (2, 0) and e_val.numel() == 0 and e_nhop.shape == (0, 4)
+    with pytest.raises(IndexError):
+        tg.batch_edges([n])
     # and the model consumes them directly
     from recon_b200 import KGraph
     kg = KGraph(idx, val, nhop.long(), n, r, device=dev())
     assert kg.n_edges == len(want_val) + len(want_nhop)
+
+
+# ---- argument checks the raw-pointer C ABI cannot do -------------------------------------------
+def test_mismatched_tables_raise_instead_of_reading_out_of_bounds():
+    from recon_b200 import SpKBGATModified, KGraph, SpGraphAttentionLayer
+    from recon_b200.synth import make_kg
+    n, r = 50, 5
+    edge, etype, _ = make_kg(n, 300, r, seed=1)
+    model = SpKBGATModified(torch.randn(n, 8), torch.randn(r, 8), [6, 12], [6, 12], 0.0, 0.2, [2, 2], None).to(dev())
+    big = KGraph(edge, etype, None, n + 7, r, device=dev())                 # graph built for more nodes than the model has
+    with pytest.raises(IndexError):
+        model(None, torch.arange(n), big, None)
+    more_rel = KGraph(edge, etype, None, n, r + 3, device=dev())            # ... or for more relations
+    with pytest.raises(IndexError):
+        model(None, torch.arange(n), more_rel, None)
+    with pytest.raises(IndexError):                                         # batch_test with a shorter entity table
+        model.batch_test(None, torch.arange(n), (edge, etype), None, torch.randn(n - 1, 8, device=dev()))
+    layer = SpGraphAttentionLayer(n, 8, 6, 4, 0.0, 0.2).to(dev())
+    with pytest.raises(RuntimeError):                                       # fewer edge embeddings than edges
+        layer(torch.randn(n, 8, device=dev()), edge.to(dev()), torch.randn(299, 4, device=dev()), None, None)
+
+
+def test_forward_rebinds_entity_data_like_the_reference():
+    """models.py:160-161 assigns a NEW tensor to entity_embeddings.data: a tensor the caller shares with the Parameter must
+    keep its values (the reference builds several models from one global embedding tensor)."""
+    from recon_b200 import SpKBGATModified
+    from recon_b200.synth import make_kg
+    n, r = 40, 4
+    edge, etype, _ = make_kg(n, 200, r, seed=2)
+    init = (torch.randn(n, 8) * 3).to(dev())
+    keep = init.clone()
+    model = SpKBGATModified(init, torch.randn(r, 8).to(dev()), [6, 12], [6, 12], 0.0, 0.2, [2, 2], None).to(dev())
+    model(None, torch.arange(n), (edge, etype), None)
+    assert torch.equal(init, keep)
+    norms = model.entity_embeddings.detach().norm(dim=1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=1e-5)
