@@ -218,9 +218,25 @@ __global__ void nhop_rows_kernel(const int* __restrict__ acc, int na, const int*
     out[4 * i + 3] = ut[cc];
 }
 
+// Scratch is carved out of a few large blocks obtained from the caller's allocator (one callback per ~64 MB instead of one
+// per array); results are separate allocations so that the caller can hand them out as tensors of their own.
 struct Arena {
     spk_alloc_fn fn; void* ctx; bool failed = false;
+    char* cur = nullptr; size_t left = 0;
+    static constexpr size_t BLOCK = 64u << 20;
     template <class T> T* get(long n) {
+        size_t bytes = ((size_t)(n > 0 ? n : 1) * sizeof(T) + 255) & ~(size_t)255;
+        if (bytes > left) {
+            const size_t want = bytes > BLOCK ? bytes : BLOCK;
+            cur = reinterpret_cast<char*>(fn(ctx, (int64_t)want));
+            if (!cur) { failed = true; left = 0; return nullptr; }
+            left = want;
+        }
+        T* p = reinterpret_cast<T*>(cur);
+        cur += bytes; left -= bytes;
+        return p;
+    }
+    template <class T> T* result(long n) {
         void* p = fn(ctx, (int64_t)(n > 0 ? n : 1) * (int64_t)sizeof(T));
         if (!p) failed = true;
         return reinterpret_cast<T*>(p);
@@ -323,14 +339,14 @@ extern "C" int spk_nhop_build(const spk_triple_graph* g, const int64_t* sources,
     // ---- batch adjacency
     if (int rc = exscan(ce, K1, offe, ar, s)) return rc;
     if (int rc = read_int(offe + K1, s, &E1)) return rc;
-    res->adj_idx = ar.get<int64_t>(2 * E1); res->adj_val = ar.get<int64_t>(E1); res->e1 = E1;
+    res->adj_idx = ar.result<int64_t>(2 * E1); res->adj_val = ar.result<int64_t>(E1); res->e1 = E1;
     if (ar.failed) { set_error("nhop_build: allocation failed"); return 4; }
     if (E1 > 0) {
         adjacency_kernel<<<blocks(E1), 256, 0, s>>>(offe, (int)K1, (int)E1, l1_b, l1_a, l1_m, s32, g->ugs, g->rs,
                                                      reinterpret_cast<long long*>(res->adj_idx), reinterpret_cast<long long*>(res->adj_val));
         if (int rc = check_launch("nhop_adjacency")) return rc;
     }
-    if (!want_nhop) { res->nhop = ar.get<int32_t>(0); return ar.failed ? 4 : 0; }
+    if (!want_nhop) { res->nhop = ar.result<int32_t>(0); return ar.failed ? 4 : 0; }
     // ---- level-2 candidates + blockers, stable sort by (slot, node)
     if (int rc = exscan(cnt2, K1, off2, ar, s)) return rc;
     if (int rc = read_int(off2 + K1, s, &Cn)) return rc;
@@ -378,14 +394,14 @@ extern "C" int spk_nhop_build(const spk_triple_graph* g, const int64_t* sources,
                 acc = acc2; NA = NA2;
             }
         }
-        res->nhop = ar.get<int32_t>(4 * NA); res->e2 = NA;
+        res->nhop = ar.result<int32_t>(4 * NA); res->e2 = NA;
         if (ar.failed) { set_error("nhop_build: allocation failed"); return 4; }
         if (NA > 0) {
             nhop_rows_kernel<<<blocks(NA), 256, 0, s>>>(acc, (int)NA, c_l1, c_c, l1_b, l1_a, s32, g->ur0, g->ut, res->nhop);
             if (int rc = check_launch("nhop_rows")) return rc;
         }
     } else {
-        res->nhop = ar.get<int32_t>(0);
+        res->nhop = ar.result<int32_t>(0);
     }
     return ar.failed ? 4 : 0;
 }
