@@ -532,12 +532,18 @@ class SingleGPU:
         n, e = self.n, self.e
         h_avg = (HEADS + 1) / 2.0
         algs = {
+            # K2: per edge the P2~[j] row (4 Dt) + col / type indices (8) (+4 per 2-hop edge); per node P1~ read + out write
             "edge_attn_fwd": e * (4 * dt + 8) + 4 * self.e2 + n * (8 * dt),
             "edge_attn_bwd_rows": e * (4 * dt + 8 + 8 * h_avg) + 4 * self.e2 + n * (20 * dt),
             "edge_attn_bwd_segments:cols": e * (4 * dt + 8 + 8 * h_avg) + n * (4 * dt),
-            # split-dot backward of the projected layer (layer 2, H = 1): one C-ABI call = node pass + column pass +
-            # relation pass + sums; charged with SURVEY 8d's pass A + pass B bytes of that layer (the relation pass and
-            # the record traffic beyond 16 B/edge are not in B_alg)
+            # split-dot backward of the projected layer (layer 2, H = 1), one gather kernel per timed call:
+            #   column pass  = SURVEY 8d "pass B": per edge the dnum[i] row (4 Dt) + row index + position (8) + its record
+            #                  (8 H); per column the P2~[j] read and the dP2~[j] write (8 Dt)
+            #   relation pass: per edge the dnum[i] row again (4 Dt) + indices (8) + record (8 H); dP3~ is cache resident
+            #   node pass    : per node dOut, out read and dnum, dP1~ written (16 Dt)
+            "edge_attn_bwd_split:cols": e * (4 * dt + 8 + 8 * 1) + n * (8 * dt),
+            "edge_attn_bwd_split:rels": e * (4 * dt + 8 + 8 * 1),
+            "edge_attn_bwd_split:node": n * (16 * dt),
             "edge_attn_bwd_split": e * (8 * dt + 16 + 16 * 1) + n * (24 * dt),
         }
         cand = {}
@@ -555,10 +561,14 @@ class SingleGPU:
         ms_launch = cand[top][0] / cand[top][1]
         achieved = algs[top] / (ms_launch * 1e-3) / 1e9
         traffic = None                         # dram__bytes_read+write per launch from the committed ncu capture (profiles/)
-        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tj):
             traffic = json.load(open(tj)).get(f"c2:{top}") if (self.n, self.e) == (2_000_000, 20_000_000) else None
-        return {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        cuda_kernels = {"edge_attn_fwd": "edge_fwd_stream_kernel<2,1,0,*> (rows + hub tasks) + edge_fwd_hub_finalize_kernel",
+                        "edge_attn_bwd_split:cols": "split_cols_kernel<2,1,4,4> (+ split_cols_tasks_kernel for hub columns)",
+                        "edge_attn_bwd_split:rels": "split_rels_tasks_kernel<2,1,4,4> (+ split_rels_kernel) + split_sum_kernel (rows)",
+                        "edge_attn_bwd_split:node": "bwd_node_kernel<2,1>"}
+        return {"bound": "hbm", "kernel": top, "cuda_kernels": cuda_kernels.get(top, top), "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms_launch,
                 "alg_bytes_per_launch": algs[top],
                 "all": {k: {"ms_per_launch": cand[k][0] / cand[k][1], "gbs": algs[k] / (cand[k][0] / cand[k][1] * 1e-3) / 1e9}

@@ -176,10 +176,11 @@ int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* args, spk_stream_t st
  *      rec4 [E, H, 4] and dsv [E, H] are scratch in CSR order.
  *      `phases` (0 = all) selects what one call launches, so that a multi-GPU caller can start the reduce-scatter of the
  *      partial dP2~ right after the column pass and overlap it with the rest:
- *        1 = node pass + column pass (G, rowsc, dP1~ without its q slot, rec4, dP2~ without its q slot)
- *        2 = relation pass (dsv, dP3~) + row sums of ds (q slot of dP1~)
- *        4 = column sums of ds: into the q slot of dP2~, or, when `colsum` is given, into colsum[col * ld_colsum + h]
- *      Phases must run in the order 1, 2, 4 on one stream. ---- */
+ *        1 = node pass (G, rowsc, dP1~ without its q slot)
+ *        2 = column pass (rec4, dP2~ without its q slot)
+ *        4 = relation pass (dsv, dP3~) + row sums of ds (q slot of dP1~)
+ *        8 = column sums of ds: into the q slot of dP2~, or, when `colsum` is given, into colsum[col * ld_colsum + h]
+ *      Phases must run in the order 1, 2, 4, 8 on one stream (any grouping: 3 then 12, or one call with 0 = 15). ---- */
 typedef struct {
     spk_edge_bwd_fused_args base;                /* csc_t2 must be null; rec unused; col_hub as there; row_hub.partial [n_tasks, >= 4] */
     const int32_t* relptr; const int32_t* rel_row; const int32_t* rel_pos;

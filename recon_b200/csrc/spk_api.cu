@@ -259,9 +259,9 @@ int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* q, spk_stream_t strea
         set_error("edge_attn_bwd_split: row hub partial buffer [n_tasks, >= 4] required");
         return 1;
     }
-    a.phases = q->phases == 0 ? 7 : q->phases;
+    a.phases = q->phases == 0 ? 15 : q->phases;
     a.colsum = q->colsum; a.ld_colsum = q->ld_colsum;
-    if (a.phases < 0 || a.phases > 7 || (a.colsum && a.ld_colsum < q->base.geom.n_heads)) {
+    if (a.phases < 0 || a.phases > 15 || (a.colsum && a.ld_colsum < q->base.geom.n_heads)) {
         set_error("edge_attn_bwd_split: bad phases / colsum");
         return 1;
     }

@@ -50,7 +50,7 @@ struct BwdSplitArgs {
     float alpha;
     HubTasks col_hub;                     // partial: [n_tasks, >= Wd]
     HubTasks rel_hub;                     // partial: [n_tasks, >= Wd]
-    int phases;                           // bit 0: node + column pass, bit 1: relation pass + row sums, bit 2: column sums
+    int phases;                           // bit 0: node pass, 1: column pass, 2: relation pass + row sums, 3: column sums
     float* colsum; long ld_colsum;        // optional destination of the column sums instead of the q slot of dP2~
 };
 

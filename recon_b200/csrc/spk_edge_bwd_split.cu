@@ -425,6 +425,8 @@ template <int NCH, int HT>
 int launch_split_t(const BwdSplitArgs& a, cudaStream_t s) {
     if (a.phases & 1) {
         if (int rc = launch_edge_bwd_node(a.f, s)) return rc;
+    }
+    if (a.phases & 2) {
         if (int rc = launch_split_pass<NCH, HT>(a, s, 0)) return rc;
         if (a.col_hub.n_tasks > 0) {
             SegGatherArgs fa;
@@ -433,7 +435,7 @@ int launch_split_t(const BwdSplitArgs& a, cudaStream_t s) {
             if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
         }
     }
-    if (a.phases & 2) {
+    if (a.phases & 4) {
         if (int rc = launch_split_pass<NCH, HT>(a, s, 1)) return rc;
         if (a.rel_hub.n_tasks > 0) {
             SegGatherArgs fa;
@@ -444,7 +446,7 @@ int launch_split_t(const BwdSplitArgs& a, cudaStream_t s) {
         // q slot of dP1~ (rows: contiguous records)
         if (int rc = launch_sums<HT>(a.f.rowptr, nullptr, a.dsv, a.g.H, a.f.n_rows, a.f.row_hub, a.f.dP1, a.f.ldd1, a.g.Dt4 * 4, s)) return rc;
     }
-    if (a.phases & 4) {
+    if (a.phases & 8) {
         // q slot of dP2~ (columns: records through csc_pos), or the caller's separate column-sum array
         if (a.colsum) return launch_sums<HT>(a.colptr, a.csc_pos, a.dsv, a.g.H, a.n_cols, a.col_hub, a.colsum, a.ld_colsum, 0, s);
         return launch_sums<HT>(a.colptr, a.csc_pos, a.dsv, a.g.H, a.n_cols, a.col_hub, a.dP2, a.ldd2, a.g.Dt4 * 4, s);

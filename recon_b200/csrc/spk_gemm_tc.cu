@@ -359,6 +359,232 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+
+// ---- 2-CTA (cta_group::2) helpers --------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {      // acquire at cluster scope
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAITC:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONEC;\n\t"
+        "bra LAB_WAITC;\n\t"
+        "DONEC:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// arrive (release at cluster scope) on the mbarrier at the same CTA-relative address in the CTA of cluster rank `rank`
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+
+// Pair-CTA variant of gemm_nn_tc_kernel (launched as clusters of 2 = one CTA pair on a TPC). The pair owns a 256-row M tile:
+// the CTA of cluster rank r holds rows [128 r, 128 r + 128) of A (raw + lo tiles, split by its own splitter warps) and HALF
+// of every weight tile (rows [r BN/2, (r+1) BN/2) of the K-major B_hi / B_lo tiles); one thread of the leader CTA (rank 0)
+// issues tcgen05.mma.cta_group::2 (M = 256, N = BN), which reads A from each CTA's own shared memory and each half of B once
+// for both tensor cores, so the weight tiles cost half the TMA writes and half the operand reads per SM. Accumulators: rows
+// of the CTA's M half in its own TMEM. Barriers: every CTA has its own full / empty / tfull; conv and tempty live in the
+// leader (peer warps arrive remotely, cluster-scope release / acquire); the leader's commits are multicast to both CTAs.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_nn_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[3 * TC_MAX_STAGES + 4];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int b_rows = p.BN / 2;
+    const uint32_t b_half = (uint32_t)b_rows * 128u;
+    const uint32_t stage_bytes = 2u * TC_A_TILE + 2u * b_half;
+    auto a_hi = [&](int s) { return base + (uint32_t)s * stage_bytes; };
+    auto a_lo = [&](int s) { return base + (uint32_t)s * stage_bytes + TC_A_TILE; };
+    auto b_hi = [&](int s) { return base + (uint32_t)s * stage_bytes + 2u * TC_A_TILE; };
+    auto b_lo = [&](int s) { return base + (uint32_t)s * stage_bytes + 2u * TC_A_TILE + b_half; };
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto conv = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+    auto empty = [&](int s) { return bar0 + 8u * (2 * TC_MAX_STAGES + s); };
+    auto tfull = [&](int a) { return bar0 + 8u * (3 * TC_MAX_STAGES + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (3 * TC_MAX_STAGES + 2 + a); };
+
+    const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    const long m_pairs = (p.M + 2 * TC_BM - 1) / (2 * TC_BM);
+    const long total = m_pairs * p.n_tiles_n;
+    const long first = blockIdx.x / 2, stride = gridDim.x / 2;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 256); mbar_init(empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                           // ---- TMA producer (both CTAs, own halves)
+            uint32_t it = 0;
+            for (long tile = first; tile < total; tile += stride) {
+                const int m0 = (int)((tile / p.n_tiles_n) * 2 + crank) * TC_BM;
+                const int n0 = (int)(tile % p.n_tiles_n) * p.BN + (int)crank * b_rows;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait_cluster(empty(s), ph ^ 1u);           // the leader's MMAs have released this stage in both CTAs
+                    mbar_arrive_expect_tx(full(s), TC_A_TILE + 2u * b_half);
+                    tma_load_2d(a_hi(s), &tmA, full(s), kb * TC_BK, m0);
+                    tma_load_2d(b_hi(s), &tmBhi, full(s), kb * TC_BK, n0);
+                    tma_load_2d(b_lo(s), &tmBlo, full(s), kb * TC_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && crank == 0) {                             // ---- MMA issuer (leader CTA only)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((2 * TC_BM) >> 4) << 24);
+            uint32_t it = 0, tl = 0;
+            for (long tile = first; tile < total; tile += stride, ++tl) {
+                const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+                mbar_wait_cluster(tempty(acc), aph ^ 1u);           // both CTAs' epilogues have drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256u;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (it / p.stages) & 1u;
+                    mbar_wait(full(s), ph);                         // my tiles landed
+                    mbar_wait_cluster(conv(s), ph);                 // both CTAs: tiles landed and A_lo written
+                    tc_fence_after();
+                    const uint64_t dah = make_kmajor_sw128_desc(a_hi(s)), dal = make_kmajor_sw128_desc(a_lo(s));
+                    const uint64_t dbh = make_kmajor_sw128_desc(b_hi(s)), dbl = make_kmajor_sw128_desc(b_lo(s));
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        if (kb * TC_BK + ks * 8 >= p.K) break;
+                        const uint64_t o = (uint64_t)(2 * ks);
+                        tc_mma2_tf32(d_tmem, dal + o, dbh + o, idesc, (kb | ks) != 0);
+                        tc_mma2_tf32(d_tmem, dah + o, dbl + o, idesc, 1u);
+                        tc_mma2_tf32(d_tmem, dah + o, dbh + o, idesc, 1u);
+                    }
+                    tc_commit2_mc(empty(s), (uint16_t)3);           // frees the stage in both CTAs
+                }
+                tc_commit2_mc(tfull(acc), (uint16_t)3);             // accumulators complete -> both epilogues
+            }
+        }
+    } else if (warp < 6) {                                         // ---- splitter (both CTAs): A_lo beside the raw tile
+        const int t = threadIdx.x - 64;
+        uint32_t it = 0;
+        for (long tile = first; tile < total; tile += stride) {
+            for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (it / p.stages) & 1u;
+                mbar_wait(full(s), ph);
+                const uint32_t hi0 = a_hi(s), lo0 = a_lo(s);
+#pragma unroll
+                for (int i = 0; i < TC_A_TILE / 16 / 128; ++i) {
+                    const uint32_t off = (uint32_t)(t + 128 * i) * 16u;
+                    float4 x;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi0 + off));
+                    float4 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_remote(conv(s), 0u);                    // the leader's barrier counts both CTAs' splitter threads
+            }
+        }
+    } else {                                                       // ---- epilogue (warps 6..9, both CTAs): TMEM -> smem -> TMA
+        const int q = warp & 3;
+        const uint32_t stg0 = base + (uint32_t)p.stages * stage_bytes + (uint32_t)q * 8192u;
+        uint32_t tl = 0, sb = 0;
+        for (long tile = first; tile < total; tile += stride, ++tl) {
+            const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+            const int row0 = (int)((tile / p.n_tiles_n) * 2 + crank) * TC_BM + q * 32;
+            const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
+            mbar_wait_cluster(tfull(acc), aph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (p.act) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(tc_elu(__uint_as_float(r[j])));
+                }
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const uint32_t stg = stg0 + sb * 4096u;
+                const uint32_t rowaddr = stg + (uint32_t)lane * 128u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t a = rowaddr + (uint32_t)((j ^ (lane & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(r[4 * j]), "r"(r[4 * j + 1]),
+                                 "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && row0 < p.M) {
+                    if (p.accumulate)
+                        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmC), "r"(n0 + c0), "r"(row0), "r"(stg) : "memory");
+                    else
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                                     ::"l"(&tmC), "r"(n0 + c0), "r"(row0), "r"(stg) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                sb ^= 1u;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(tempty(acc), 0u);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // Bt_hi/Bt_lo[n, k] = split(B[k, n]) : transposed (K-major), zero padded to ldt
 __global__ void tc_prepare_b_kernel(const float* __restrict__ B, long ldb, int K, int N, float* __restrict__ hi,
                                     float* __restrict__ lo, int ldt) {
@@ -415,6 +641,13 @@ static int tc_cluster() {
     return v;
 }
 
+// SPK_TC_PAIR=0 disables the pair-CTA (cta_group::2) kernel
+static int tc_pair() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
 // SPK_TC_RAW_HI=0 restores the explicit hi rewrite in the splitter (default: the raw tile is the hi operand)
 static int tc_raw_hi() {
     static int v = -1;
@@ -458,6 +691,47 @@ int gemm_nn_tc(const float* A, long lda, const float* B, long ldb, float* C, lon
     const long m_tiles = (M + TC_BM - 1) / TC_BM;
     // clusters of 2 share each weight tile (half the L2 -> SM traffic of the re-streamed weights); worth it once every SM
     // has work either way
+    // pair-CTA kernel (M = 256 per CTA pair, each weight tile split over the pair): needs the TMA epilogue, the raw tile
+    // as hi operand, BN/2 a multiple of 8 rows, and enough tiles that every SM has work either way
+    const bool pair = tc_pair() && c_tma && tc_raw_hi() && (BN % 16 == 0) && m_tiles * n_tiles_n >= 2L * sms;
+    if (pair) {
+        const int half_tile = BN / 2 * 128;
+        const int stage2 = 2 * TC_A_TILE + 2 * half_tile;
+        int stages2 = (225 * 1024 - 1024 - staging) / stage2;
+        if (stages2 > TC_MAX_STAGES) stages2 = TC_MAX_STAGES;
+        const int smem2 = stages2 * stage2 + staging + 1024;
+        CUtensorMap tA, tBh, tBl, tC;
+        if (int rc = make_map(&tA, A, M, K, lda, TC_BM)) return rc;
+        if (int rc = make_map(&tBh, bhi, N, K, ldt, BN / 2)) return rc;
+        if (int rc = make_map(&tBl, blo, N, K, ldt, BN / 2)) return rc;
+        if (int rc = make_map(&tC, C, M, N, ldc, 32)) return rc;
+        TcParams q;
+        q.C = C; q.ldc = ldc; q.M = M; q.N = N; q.K = K; q.BN = BN; q.n_tiles_n = n_tiles_n; q.stages = stages2;
+        q.accumulate = accumulate; q.act = act; q.c_vec = c_vec; q.c_tma = 1; q.raw_hi = 1; q.cs = 2;
+        static SmemLimit lim2;
+        if (lim2.ensure(gemm_nn_tc2_kernel, 226 * 1024) != cudaSuccess) {
+            set_error("gemm_tc: cannot raise dynamic shared memory limit");
+            (void)cudaGetLastError();
+            return 3;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)sms / 2 * 2); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = (size_t)smem2; cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        static int pairs_resident[64] = {};
+        int nc = (dev >= 0 && dev < 64) ? pairs_resident[dev] : 0;
+        if (nc == 0) {
+            if (cudaOccupancyMaxActiveClusters(&nc, gemm_nn_tc2_kernel, &cfg) != cudaSuccess || nc < 1) { (void)cudaGetLastError(); nc = sms / 4; }
+            if (dev >= 0 && dev < 64) pairs_resident[dev] = nc;
+        }
+        const long pair_tiles = ((m_tiles + 1) / 2) * n_tiles_n;
+        const long np = pair_tiles < nc ? pair_tiles : nc;
+        cfg.gridDim = dim3((unsigned)(2 * np));
+        (void)cudaLaunchKernelEx(&cfg, gemm_nn_tc2_kernel, tA, tBh, tBl, tC, q);
+        return check_launch("gemm_nn_tc2");
+    }
     const int cs = (tc_cluster() == 2 && !accumulate && m_tiles * n_tiles_n >= 2L * sms) ? 2 : 1;
 
     CUtensorMap tmA, tmBhi, tmBlo, tmC;

@@ -252,16 +252,23 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
         part1 = _hub_partial(graph.row_hubs, 4, dev)                # row sums of ds over hub rows
         graph.row_hubs.fill(q.base.row_hub, part1, 4)
         if after_columns is None:
-            _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+            if lib.timing is None:
+                _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+            else:                           # bench.py's per-kernel timing pass: one pass (= one gather kernel) per call
+                for ph, tag in ((1, "node"), (2, "cols"), (4, "rels"), (8, "colsums")):
+                    q.phases = ph
+                    _lib.current_tag = tag
+                    _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+                _lib.current_tag = ""
             del keep, part3, part1
             return False
-        q.phases = 1
-        _lib.current_tag = "cols"
+        q.phases = 3
+        _lib.current_tag = "node+cols"
         _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
         after_columns()
-        q.phases = 6
+        q.phases = 12
         q.colsum = colsum.data_ptr(); q.ld_colsum = colsum.stride(0)
-        _lib.current_tag = "rels"
+        _lib.current_tag = "rels+sums"
         _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
         _lib.current_tag = ""
         del keep, part3, part1

@@ -466,3 +466,31 @@ def test_forward_rebinds_entity_data_like_the_reference():
     assert torch.equal(init, keep)
     norms = model.entity_embeddings.detach().norm(dim=1)
     assert torch.allclose(norms, torch.ones_like(norms), atol=1e-5)
+
+
+def test_phased_split_backward_is_bit_identical_to_one_call():
+    """bench.py's per-kernel timing pass issues the split-dot backward as four phased calls (node / columns / relations /
+    column sums, include/spkbgat.h spk_edge_bwd_split_args.phases): same kernels, same order, same bits."""
+    from recon_b200 import SpKBGATModified, profiler
+    from recon_b200.synth import make_kg
+    n, r = 3000, 17
+    edge, etype, _ = make_kg(n, 40000, r, alpha=1.1, seed=5)
+    torch.manual_seed(3)
+    model = SpKBGATModified(torch.randn(n, 50), torch.randn(r, 50), [100, 200], [100, 200], 0.0, 0.2, [2, 2], None).to(dev())
+    ent0 = model.entity_embeddings.detach().clone()
+    graph = model.prepare_graph((edge.to(dev()), etype.to(dev())), None)
+
+    def run():
+        model.entity_embeddings.data = ent0.clone()
+        model.zero_grad(set_to_none=True)
+        out_e, out_r, _ = model(None, torch.arange(n), graph, None)
+        (out_e.sum() + (out_r * out_r).sum()).backward()
+        return {k: v.grad.clone() for k, v in model.named_parameters() if v.grad is not None}
+
+    a = run()
+    profiler.enable()
+    b = run()
+    prof = profiler.disable()
+    assert {"edge_attn_bwd_split:node", "edge_attn_bwd_split:cols", "edge_attn_bwd_split:rels",
+            "edge_attn_bwd_split:colsums"} <= set(prof)
+    assert all(torch.equal(a[k], b[k]) for k in a)
