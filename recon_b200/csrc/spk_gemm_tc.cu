@@ -400,7 +400,7 @@ __device__ __forceinline__ void tc_mma2_tf32(uint32_t d_tmem, uint64_t adesc, ui
 // issues tcgen05.mma.cta_group::2 (M = 256, N = BN), which reads A from each CTA's own shared memory and each half of B once
 // for both tensor cores, so the weight tiles cost half the TMA writes and half the operand reads per SM. Accumulators: rows
 // of the CTA's M half in its own TMEM. Barriers: every CTA has its own full / empty / tfull; conv and tempty live in the
-// leader (peer warps arrive remotely, cluster-scope release / acquire); the leader's commits are multicast to both CTAs.
+// leader (one lane per peer warp arrives remotely, cluster-scope release / acquire); the leader's commits are multicast to both CTAs.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_nn_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
@@ -434,7 +434,7 @@ gemm_nn_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
-        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 256); mbar_init(empty(s), 1); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(conv(s), 8); mbar_init(empty(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -478,7 +478,7 @@ gemm_nn_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const int s = it % p.stages;
                     const uint32_t ph = (it / p.stages) & 1u;
                     mbar_wait(full(s), ph);                         // my tiles landed
-                    mbar_wait_cluster(conv(s), ph);                 // both CTAs: tiles landed and A_lo written
+                    mbar_wait_cluster(conv(s), ph);                 // both CTAs (4 + 4 splitter warps): tiles landed, A_lo written
                     tc_fence_after();
                     const uint64_t dah = make_kmajor_sw128_desc(a_hi(s)), dal = make_kmajor_sw128_desc(a_lo(s));
                     const uint64_t dbh = make_kmajor_sw128_desc(b_hi(s)), dbl = make_kmajor_sw128_desc(b_lo(s));
@@ -517,7 +517,8 @@ gemm_nn_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(lo0 + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive_remote(conv(s), 0u);                    // the leader's barrier counts both CTAs' splitter threads
+                __syncwarp();                                       // one cluster-scope release per warp, not per thread
+                if (lane == 0) mbar_arrive_remote(conv(s), 0u);     // (the per-thread form stalled the splitters on membar)
             }
         }
     } else {                                                       // ---- epilogue (warps 6..9, both CTAs): TMEM -> smem -> TMA
@@ -636,16 +637,18 @@ int gemm_tc_ldt(int K) { return (K + 3) / 4 * 4; }
 // L2 -> SM re-stream of the weights: profiles/README.md, round 2) and the C += (TMA reduce-add) epilogue lost updates on
 // short-K shapes in this mode, so it is never combined with `accumulate`.
 static int tc_cluster() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SPK_TC_CLUSTER"); v = (e && e[0] == '2') ? 2 : 1; }
-    return v;
+    const char* e = getenv("SPK_TC_CLUSTER");
+    return (e && e[0] == '2') ? 2 : 1;
 }
 
-// SPK_TC_PAIR=0 disables the pair-CTA (cta_group::2) kernel
+// SPK_TC_PAIR=1 selects the pair-CTA (cta_group::2) kernel. EXPERIMENTAL, off by default: correct (tests/test_gpu_parity.py
+// runs the GEMM tests in this mode too) and it cuts the L2 -> SM operand traffic by 39 % (ncu: 16.1 -> 9.9 GB on
+// [2M,200]x[200,416]), but it is 5-40 % SLOWER on every product of the step: 3xTF32 re-reads each weight half 12 times per
+// k-block and in pair mode half of those reads cross the SM-to-SM path (profiles/README.md, round 2). Read on every call so
+// tests can toggle it.
 static int tc_pair() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SPK_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v;
+    const char* e = getenv("SPK_TC_PAIR");
+    return (e && e[0] == '1') ? 1 : 0;
 }
 
 // SPK_TC_RAW_HI=0 restores the explicit hi rewrite in the splitter (default: the raw tile is the hi operand)

@@ -102,13 +102,18 @@ def test_kgraph_empty():
 
 
 # ---- K1/K5: GEMMs ---------------------------------------------------------------------------------
-@pytest.fixture(params=["tc", "simt"])
-def gemm_path(request):
-    """Run the test once on the tcgen05 3xTF32 GEMM and once on the exact-fp32 SIMT GEMM."""
+@pytest.fixture(params=["tc", "simt", "tc-pair", "tc-cluster"])
+def gemm_path(request, monkeypatch):
+    """Run the test on the tcgen05 3xTF32 GEMM, on the exact-fp32 SIMT GEMM, and on the two experimental NN variants
+    (pair-CTA cta_group::2 kernel, 2-CTA clusters with multicast weight tiles; both off by default, see spk_gemm_tc.cu)."""
     from recon_b200 import functional as SF
     old = SF.USE_TC
-    SF.USE_TC = request.param == "tc"
-    yield request.param
+    SF.USE_TC = request.param != "simt"
+    if request.param == "tc-pair":
+        monkeypatch.setenv("SPK_TC_PAIR", "1")
+    if request.param == "tc-cluster":
+        monkeypatch.setenv("SPK_TC_CLUSTER", "2")
+    yield "simt" if request.param == "simt" else "tc"
     SF.USE_TC = old
 
 
