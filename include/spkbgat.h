@@ -57,6 +57,10 @@ int spk_edges_concat(const int64_t* edge /*[2,E1]*/, int64_t e1, const int64_t* 
                      const int64_t* nhop /*[E2,4] = s,r1,r2,t*/, int64_t e2,
                      int32_t* row, int32_t* col, int32_t* t1, int32_t* t2 /*null if e2==0*/,
                      int64_t n_nodes, int64_t n_rel, int32_t* err_flag, spk_stream_t stream);
+/* HOST pointers: dst[i] = (int32) src[i * stride], range-checked against [lo, hi) by n_threads host threads (0 = all):
+ * packs the reference API's int64 index tensors into a pinned int32 staging buffer so that half the bytes cross PCIe;
+ * returns 5 if a value is out of range. Used by recon_b200.KGraph for host-resident edge tensors. */
+int spk_pack_index_host(const int64_t* src, int64_t n, int64_t stride, int64_t lo, int64_t hi, int32_t* dst, int32_t n_threads);
 int spk_iota_i32(int32_t* v, int64_t n, spk_stream_t stream);
 int64_t spk_sort_workspace_bytes(int64_t n);
 /* stable LSD radix sort of (key,value) pairs on the low key_bits bits; result_in_tmp tells which buffers hold it */

@@ -148,6 +148,7 @@ SIGNATURES = {
     "spk_last_error": (C.c_char_p, []),
     "spk_launch_count": (_I64, []),
     "spk_edges_concat": (_I32, [_VP, _I64, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _I64, _I64, _VP, _VP]),
+    "spk_pack_index_host": (_I32, [_VP, _I64, _I64, _I64, _I64, _VP, _I32]),
     "spk_iota_i32": (_I32, [_VP, _I64, _VP]),
     "spk_sort_workspace_bytes": (_I64, [_I64]),
     "spk_sort_pairs": (_I32, [_VP, _VP, _VP, _VP, _I64, _I32, _VP, C.POINTER(_I32), _VP]),

@@ -329,4 +329,38 @@ int spk_import_json(const char* path, float* out, int64_t rows, int64_t width, i
     return 0;
 }
 
+
+/* Host staging of the edge list (HOST pointers, no GPU work): int64 index column (stride in elements, e.g. one column
+ * of the [E2,4] 2-hop rows) -> int32, range-checked against [lo, hi), by n_threads host threads (0 = all cores). The int64
+ * tensors of the reference API carry 32 bits of information per element; packing them into pinned memory halves the
+ * bytes that cross PCIe. Returns 0, or 5 if a value is out of range (IndexError in the reference). */
+int spk_pack_index_host(const int64_t* src, int64_t n, int64_t stride, int64_t lo, int64_t hi, int32_t* dst, int32_t n_threads) {
+    if (n < 0 || stride < 1 || (n > 0 && (!src || !dst))) { spk::set_error("pack_index_host: bad arguments"); return 1; }
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 64));
+    if (n < (1 << 18)) nt = 1;
+    std::atomic<int> bad{0};
+    auto work = [&](int64_t b, int64_t e) {
+        int local_bad = 0;
+        for (int64_t i = b; i < e; ++i) {
+            const int64_t v = src[i * stride];
+            local_bad |= (v < lo) | (v >= hi);
+            dst[i] = (int32_t)v;
+        }
+        if (local_bad) bad.store(1, std::memory_order_relaxed);
+    };
+    if (nt == 1) work(0, n);
+    else {
+        std::vector<std::thread> th;
+        const int64_t chunk = (n + nt - 1) / nt;
+        for (int t = 0; t < nt; ++t) {
+            const int64_t b = std::min(n, (int64_t)t * chunk), e = std::min(n, b + chunk);
+            if (b < e) th.emplace_back(work, b, e);
+        }
+        for (auto& x : th) x.join();
+    }
+    if (bad.load()) { spk::set_error("pack_index_host: index outside [%lld, %lld)", (long long)lo, (long long)hi); return 5; }
+    return 0;
+}
+
 }  // extern "C"

@@ -275,15 +275,16 @@ class PartitionedKBGAT:
         relation rebuild, forward + backward, loss read-back. Returns (seconds per step, h2d bytes per step)."""
         import time
         from .graph import KGraph
-        host = tuple(t.cpu().pin_memory() for t in self._local_edges_dev)
-        h2d = sum(t.numel() * t.element_size() for t in host)
+        host = tuple(t.cpu() for t in self._local_edges_dev)
+        n_loc_edges = host[0].shape[1] + host[2].shape[0]
+        h2d = 4 * (4 if host[2].numel() else 3) * n_loc_edges          # int32 staging of the int64 tensors (graph.py)
         res = torch.empty(1, dtype=torch.float32).pin_memory()
         times = []
         for i in range(steps + 1):
             dist.barrier(group=self.group)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            e_loc, t_loc, nh_loc = (t.to(self.device, non_blocking=True) for t in host)
+            e_loc, t_loc, nh_loc = host
             graph = KGraph(e_loc, t_loc, nh_loc if nh_loc.numel() else None, self.hi - self.lo + self.part.n_ghost,
                            self.n_rel, device=self.device, n_cols=self.world * self.part.max_rows)
             graph.dist = self.graph.dist

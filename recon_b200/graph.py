@@ -120,6 +120,72 @@ def _segment_ptr(sorted_keys, n_seg):
     return ptr
 
 
+_STAGING = {}          # device index -> {"buf": pinned int32 tensor, "event": last H2D that read it, "stream": copy stream}
+
+
+def _stage_host_edges(edge, edge_type, nhop, e1, e2, max_idx, n_rel, device):
+    """HOST int64 edge tensors -> device int32 (row, col, t1, t2) arrays + the events that mark their arrival.
+
+    The reference hands the adjacency over as int64 LongTensors (GAT/create_batch.py:433); they carry 32 bits of information
+    per element, so they are packed into a cached pinned int32 staging buffer by all host cores (spk_pack_index_host, range-
+    checked: the IndexError of the reference comes from here, before any device work) and copied array by array on a copy
+    stream: the rows travel first and the CSR sort starts as soon as they arrive, while the gather indices and the
+    relation ids are still being packed / copied. Half the PCIe bytes of copying the int64 tensors, and the layout build
+    overlaps the transfer."""
+    lib = _lib.load()
+    e = e1 + e2
+    has2 = e2 > 0
+    n_arr = 4 if has2 else 3
+    st = _STAGING.setdefault(device.index, {})
+    if st.get("buf") is None or st["buf"].numel() < n_arr * e:
+        st["buf"] = torch.empty(n_arr * e, dtype=torch.int32).pin_memory()
+        st["event"] = None
+    if st.get("stream") is None:
+        st["stream"] = torch.cuda.Stream(device=device)
+    if st.get("event") is not None:
+        st["event"].synchronize()                          # the previous build's copies have left the staging buffer
+    buf, cs = st["buf"], st["stream"]
+    main = torch.cuda.current_stream(device)
+    cs.wait_stream(main)                                   # freshly allocated device arrays may still be in use upstream
+    edge = edge.contiguous(); edge_type = edge_type.contiguous()
+    if has2:
+        nhop = nhop.contiguous()
+    # (source pointer, stride, 2-hop column, upper bound) per array, in the order the build consumes them
+    plan = [("row", edge.data_ptr(), 3, max_idx), ("col", edge.data_ptr() + 8 * e1, 0, max_idx), ("t1", edge_type.data_ptr(), 1, n_rel)]
+    out, events = {}, {}
+    for k, (name, src, hop_col, hi) in enumerate(plan):
+        seg = buf[k * e:(k + 1) * e]
+        rc = lib.spk_pack_index_host(src if e1 else None, e1, 1, 0, hi, seg.data_ptr(), 0)
+        if rc == 0 and has2:
+            rc = lib.spk_pack_index_host(nhop.data_ptr() + 8 * hop_col, e2, 4, 0, hi, seg.data_ptr() + 4 * e1, 0)
+        if rc == 5:
+            raise IndexError("edge / relation index out of range for the given entity / relation tables")
+        _lib.check(rc, "pack_index_host")
+        dev_arr = torch.empty(e, dtype=torch.int32, device=device)
+        with torch.cuda.stream(cs):
+            dev_arr.copy_(seg, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        dev_arr.record_stream(cs)
+        out[name], events[name] = dev_arr, ev
+    if has2:
+        seg = buf[3 * e:4 * e]
+        seg[:e1].fill_(-1)
+        rc = lib.spk_pack_index_host(nhop.data_ptr() + 16, e2, 4, 0, n_rel, seg.data_ptr() + 4 * e1, 0)
+        if rc == 5:
+            raise IndexError("edge / relation index out of range for the given entity / relation tables")
+        _lib.check(rc, "pack_index_host")
+        dev_arr = torch.empty(e, dtype=torch.int32, device=device)
+        with torch.cuda.stream(cs):
+            dev_arr.copy_(seg, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        dev_arr.record_stream(cs)
+        out["t2"], events["t2"] = dev_arr, ev
+    st["event"] = ev
+    return out, events
+
+
 class KGraph:
     """Device-resident segment layouts of one edge list.
 
@@ -137,32 +203,47 @@ class KGraph:
         self.n_nodes = int(n_nodes)
         self.n_cols = int(n_cols if n_cols is not None else n_nodes)
         self.n_rel = int(n_rel)
-        edge = edge.to(device=device, dtype=torch.int64).contiguous()
-        edge_type = edge_type.to(device=device, dtype=torch.int64).contiguous()
         self.e1 = int(edge.shape[1]) if edge.dim() == 2 else 0
         has2 = nhop is not None and nhop.numel() > 0
         self.e2 = int(nhop.shape[0]) if has2 else 0
-        nhop = nhop.to(device=device, dtype=torch.int64).contiguous() if has2 else None
         e = self.e1 + self.e2
         self.n_edges = e
         i32 = dict(dtype=torch.int32, device=device)
-        row = torch.empty(e, **i32); col = torch.empty(e, **i32); t1 = torch.empty(e, **i32)
-        t2 = torch.empty(e, **i32) if has2 else None
-        err = torch.zeros(1, **i32)
         max_idx = max(self.n_nodes, self.n_cols)
-        _lib.check(lib.spk_edges_concat(edge.data_ptr() if self.e1 else None, self.e1,
-                                        edge_type.data_ptr() if self.e1 else None,
-                                        nhop.data_ptr() if has2 else None, self.e2,
-                                        row.data_ptr(), col.data_ptr(), t1.data_ptr(),
-                                        t2.data_ptr() if has2 else None, max_idx, self.n_rel,
-                                        err.data_ptr(), _lib.stream_ptr()), "edges_concat")
+        main = torch.cuda.current_stream(device)
+        host = (e > 0 and not edge.is_cuda and not edge_type.is_cuda and (not has2 or not nhop.is_cuda)
+                and edge.dtype == torch.int64 and edge_type.dtype == torch.int64 and (not has2 or nhop.dtype == torch.int64))
+        if host:
+            # host-resident int64 tensors (the reference's calling convention): packed to int32 in pinned memory, copied
+            # array by array on a copy stream; every array is waited for right before its first use
+            arrs, ready = _stage_host_edges(edge, edge_type, nhop if has2 else None, self.e1, self.e2, max_idx, self.n_rel, device)
+            row, col, t1, t2 = arrs["row"], arrs["col"], arrs["t1"], arrs.get("t2")
+            err = None
+            main.wait_event(ready["row"])
+        else:
+            ready = {}
+            edge = edge.to(device=device, dtype=torch.int64).contiguous()
+            edge_type = edge_type.to(device=device, dtype=torch.int64).contiguous()
+            nhop = nhop.to(device=device, dtype=torch.int64).contiguous() if has2 else None
+            row = torch.empty(e, **i32); col = torch.empty(e, **i32); t1 = torch.empty(e, **i32)
+            t2 = torch.empty(e, **i32) if has2 else None
+            err = torch.zeros(1, **i32)
+            _lib.check(lib.spk_edges_concat(edge.data_ptr() if self.e1 else None, self.e1,
+                                            edge_type.data_ptr() if self.e1 else None,
+                                            nhop.data_ptr() if has2 else None, self.e2,
+                                            row.data_ptr(), col.data_ptr(), t1.data_ptr(),
+                                            t2.data_ptr() if has2 else None, max_idx, self.n_rel,
+                                            err.data_ptr(), _lib.stream_ptr()), "edges_concat")
         # CSR: stable sort by aggregation row
         keys, perm = sort_pairs(row, _iota(e, device), _key_bits(max_idx))
-        if int(err.item()) != 0:
+        if err is not None and int(err.item()) != 0:
             raise IndexError("edge / relation index out of range for the given entity / relation tables")
         self.row = keys
         self.perm = perm
         self.rowptr = _segment_ptr(keys, self.n_nodes)
+        for name in ("col", "t1", "t2"):
+            if name in ready:
+                main.wait_event(ready[name])
         self.col = _gather(col, perm)
         self.t1 = _gather(t1, perm)
         self.t2 = _gather(t2, perm) if has2 else None

@@ -499,3 +499,26 @@ def test_phased_split_backward_is_bit_identical_to_one_call():
     assert {"edge_attn_bwd_split:node", "edge_attn_bwd_split:cols", "edge_attn_bwd_split:rels",
             "edge_attn_bwd_split:colsums"} <= set(prof)
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("n_nhop", [0, 700])
+def test_host_staged_edges_give_the_same_layouts(n_nhop):
+    """Host-resident int64 tensors go through spk_pack_index_host + a copy stream (graph._stage_host_edges); device-resident
+    ones through spk_edges_concat. Same layouts bit for bit, twice in a row (staging buffer reuse), same IndexError."""
+    from recon_b200 import KGraph
+    from recon_b200.synth import make_kg
+    n, r = 900, 13
+    edge, etype, nhop = make_kg(n, 300_000, r, alpha=1.1, n_nhop=n_nhop, seed=4)
+    nh = nhop if n_nhop else None
+    g_dev = KGraph(edge.to(dev()), etype.to(dev()), nh.to(dev()) if n_nhop else None, n, r, device=dev())
+    for _ in range(2):
+        g_host = KGraph(edge, etype, nh, n, r, device=dev())
+        for name in ("row", "perm", "rowptr", "col", "t1", "t2", "colptr", "csc_row", "csc_pos", "csc_t1", "relptr", "rel_row", "rel_pos"):
+            a, b = getattr(g_host, name), getattr(g_dev, name)
+            assert (a is None and b is None) or torch.equal(a, b), name
+    bad = edge.clone(); bad[1, 5] = n
+    with pytest.raises(IndexError):
+        KGraph(bad, etype, nh, n, r, device=dev())
+    bad_t = etype.clone(); bad_t[7] = -1
+    with pytest.raises(IndexError):
+        KGraph(edge, bad_t, nh, n, r, device=dev())
