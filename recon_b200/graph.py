@@ -123,67 +123,73 @@ def _segment_ptr(sorted_keys, n_seg):
 _STAGING = {}          # device index -> {"buf": pinned int32 tensor, "event": last H2D that read it, "stream": copy stream}
 
 
-def _stage_host_edges(edge, edge_type, nhop, e1, e2, max_idx, n_rel, device):
-    """HOST int64 edge tensors -> device int32 (row, col, t1, t2) arrays + the events that mark their arrival.
+class _HostStager:
+    """HOST int64 edge tensors -> device int32 (row, col, t1, t2) arrays, produced on demand.
 
     The reference hands the adjacency over as int64 LongTensors (GAT/create_batch.py:433); they carry 32 bits of information
-    per element, so they are packed into a cached pinned int32 staging buffer by all host cores (spk_pack_index_host, range-
-    checked: the IndexError of the reference comes from here, before any device work) and copied array by array on a copy
-    stream: the rows travel first and the CSR sort starts as soon as they arrive, while the gather indices and the
-    relation ids are still being packed / copied. Half the PCIe bytes of copying the int64 tensors, and the layout build
-    overlaps the transfer."""
-    lib = _lib.load()
-    e = e1 + e2
-    has2 = e2 > 0
-    n_arr = 4 if has2 else 3
-    st = _STAGING.setdefault(device.index, {})
-    if st.get("buf") is None or st["buf"].numel() < n_arr * e:
-        st["buf"] = torch.empty(n_arr * e, dtype=torch.int32).pin_memory()
-        st["event"] = None
-    if st.get("stream") is None:
-        st["stream"] = torch.cuda.Stream(device=device)
-    if st.get("event") is not None:
-        st["event"].synchronize()                          # the previous build's copies have left the staging buffer
-    buf, cs = st["buf"], st["stream"]
-    main = torch.cuda.current_stream(device)
-    cs.wait_stream(main)                                   # freshly allocated device arrays may still be in use upstream
-    edge = edge.contiguous(); edge_type = edge_type.contiguous()
-    if has2:
-        nhop = nhop.contiguous()
-    # (source pointer, stride, 2-hop column, upper bound) per array, in the order the build consumes them
-    plan = [("row", edge.data_ptr(), 3, max_idx), ("col", edge.data_ptr() + 8 * e1, 0, max_idx), ("t1", edge_type.data_ptr(), 1, n_rel)]
-    out, events = {}, {}
-    for k, (name, src, hop_col, hi) in enumerate(plan):
-        seg = buf[k * e:(k + 1) * e]
-        rc = lib.spk_pack_index_host(src if e1 else None, e1, 1, 0, hi, seg.data_ptr(), 0)
-        if rc == 0 and has2:
-            rc = lib.spk_pack_index_host(nhop.data_ptr() + 8 * hop_col, e2, 4, 0, hi, seg.data_ptr() + 4 * e1, 0)
+    per element, so each array is packed into a cached pinned int32 staging buffer by all host cores (spk_pack_index_host,
+    range-checked: the reference's IndexError comes from here, before any device work) and copied on a copy stream.
+    `get(name)` packs + enqueues one array and makes the current stream wait for it, so the caller can interleave: the rows
+    travel first and their CSR sort runs on the device while the host is still packing the gather indices and the relation
+    ids. Half the PCIe bytes of copying the int64 tensors, and the layout build overlaps both the packing and the transfer."""
+
+    ORDER = ("row", "col", "t1", "t2")
+
+    def __init__(self, edge, edge_type, nhop, e1, e2, max_idx, n_rel, device):
+        self.e1, self.e2, self.e, self.device = e1, e2, e1 + e2, device
+        self.has2 = e2 > 0
+        n_arr = 4 if self.has2 else 3
+        st = _STAGING.setdefault(device.index, {})
+        if st.get("buf") is None or st["buf"].numel() < n_arr * self.e:
+            st["buf"] = torch.empty(n_arr * self.e, dtype=torch.int32).pin_memory()
+            st["event"] = None
+        if st.get("stream") is None:
+            st["stream"] = torch.cuda.Stream(device=device)
+        if st.get("event") is not None:
+            st["event"].synchronize()                      # the previous build's copies have left the staging buffer
+        self.st, self.buf, self.cs = st, st["buf"], st["stream"]
+        self.main = torch.cuda.current_stream(device)
+        # All destination arrays are allocated NOW, before any of this build's kernels is queued, and the copy stream waits for
+        # the work queued so far: memory the caching allocator hands out later could be a block that a just-queued main-stream
+        # kernel (e.g. the sort's workspace) still uses, and the copy stream would overwrite it.
+        self.dev = {name: torch.empty(self.e, dtype=torch.int32, device=device) for name in self.ORDER[:n_arr]}
+        # (Measured alternative, rejected: sending the rows as raw int64 by DMA while the cores pack the next array. The
+        # extra 80 MB on the link and the contention for host memory cost more than the packing it hides: 68.8 vs 64.5 ms.)
+        self.cs.wait_stream(self.main)
+        for t in self.dev.values():
+            t.record_stream(self.cs)
+        self.edge, self.edge_type = edge.contiguous(), edge_type.contiguous()
+        self.nhop = nhop.contiguous() if self.has2 else None
+        # name -> (1-hop source pointer, 2-hop column of [s, r1, r2, t], upper bound)
+        self.plan = {"row": (self.edge.data_ptr(), 3, max_idx), "col": (self.edge.data_ptr() + 8 * e1, 0, max_idx),
+                     "t1": (self.edge_type.data_ptr(), 1, n_rel), "t2": (None, 2, n_rel)}
+
+    def get(self, name, wait=True):
+        """Pack + queue the copy of one array; wait=False returns (array, event) and leaves the waiting to the caller."""
+        lib = _lib.load()
+        k = self.ORDER.index(name)
+        src, hop_col, hi = self.plan[name]
+        seg = self.buf[k * self.e:(k + 1) * self.e]
+        rc = 0
+        if src is not None:
+            rc = lib.spk_pack_index_host(src if self.e1 else None, self.e1, 1, 0, hi, seg.data_ptr(), 0)
+        elif self.e1:
+            seg[:self.e1].fill_(-1)                        # t2 of a 1-hop edge
+        if rc == 0 and self.has2:
+            rc = lib.spk_pack_index_host(self.nhop.data_ptr() + 8 * hop_col, self.e2, 4, 0, hi, seg.data_ptr() + 4 * self.e1, 0)
         if rc == 5:
             raise IndexError("edge / relation index out of range for the given entity / relation tables")
         _lib.check(rc, "pack_index_host")
-        dev_arr = torch.empty(e, dtype=torch.int32, device=device)
-        with torch.cuda.stream(cs):
+        dev_arr = self.dev.pop(name)
+        with torch.cuda.stream(self.cs):
             dev_arr.copy_(seg, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(cs)
-        dev_arr.record_stream(cs)
-        out[name], events[name] = dev_arr, ev
-    if has2:
-        seg = buf[3 * e:4 * e]
-        seg[:e1].fill_(-1)
-        rc = lib.spk_pack_index_host(nhop.data_ptr() + 16, e2, 4, 0, n_rel, seg.data_ptr() + 4 * e1, 0)
-        if rc == 5:
-            raise IndexError("edge / relation index out of range for the given entity / relation tables")
-        _lib.check(rc, "pack_index_host")
-        dev_arr = torch.empty(e, dtype=torch.int32, device=device)
-        with torch.cuda.stream(cs):
-            dev_arr.copy_(seg, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(cs)
-        dev_arr.record_stream(cs)
-        out["t2"], events["t2"] = dev_arr, ev
-    st["event"] = ev
-    return out, events
+            ev.record(self.cs)
+        self.st["event"] = ev
+        if not wait:
+            return dev_arr, ev
+        self.main.wait_event(ev)
+        return dev_arr
 
 
 class KGraph:
@@ -213,15 +219,15 @@ class KGraph:
         main = torch.cuda.current_stream(device)
         host = (e > 0 and not edge.is_cuda and not edge_type.is_cuda and (not has2 or not nhop.is_cuda)
                 and edge.dtype == torch.int64 and edge_type.dtype == torch.int64 and (not has2 or nhop.dtype == torch.int64))
+        stager = None
         if host:
-            # host-resident int64 tensors (the reference's calling convention): packed to int32 in pinned memory, copied
-            # array by array on a copy stream; every array is waited for right before its first use
-            arrs, ready = _stage_host_edges(edge, edge_type, nhop if has2 else None, self.e1, self.e2, max_idx, self.n_rel, device)
-            row, col, t1, t2 = arrs["row"], arrs["col"], arrs["t1"], arrs.get("t2")
+            # host-resident int64 tensors (the reference's calling convention): packed to int32 in pinned memory and copied
+            # array by array on a copy stream, each right before its first use, so the device sorts overlap the packing
+            stager = _HostStager(edge, edge_type, nhop if has2 else None, self.e1, self.e2, max_idx, self.n_rel, device)
+            row = stager.get("row")
+            col = t1 = t2 = None
             err = None
-            main.wait_event(ready["row"])
         else:
-            ready = {}
             edge = edge.to(device=device, dtype=torch.int64).contiguous()
             edge_type = edge_type.to(device=device, dtype=torch.int64).contiguous()
             nhop = nhop.to(device=device, dtype=torch.int64).contiguous() if has2 else None
@@ -241,12 +247,9 @@ class KGraph:
         self.row = keys
         self.perm = perm
         self.rowptr = _segment_ptr(keys, self.n_nodes)
-        for name in ("col", "t1", "t2"):
-            if name in ready:
-                main.wait_event(ready[name])
-        self.col = _gather(col, perm)
-        self.t1 = _gather(t1, perm)
-        self.t2 = _gather(t2, perm) if has2 else None
+        self.col = _gather(stager.get("col") if stager else col, perm)
+        self.t1 = _gather(stager.get("t1") if stager else t1, perm)
+        self.t2 = (_gather(stager.get("t2") if stager else t2, perm)) if has2 else None
         self.row_hubs = HubSet(self.rowptr)
         self.colptr = self.csc_row = self.csc_pos = self.col_hubs = self.csc_t1 = self.csc_t2 = None
         self.relptr = self.rel_row = self.rel_pos = self.rel_hubs = None
