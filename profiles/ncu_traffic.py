@@ -33,7 +33,7 @@ def main(src, dst):
     per = {}
     for r in data:
         name = r[col["Kernel Name"]]
-        short = re.sub(r"\\(.*", "", name)
+        short = name.split("(")[0]
         d = per.setdefault(short, {"n": 0, "bytes": 0.0, "ns": 0.0})
         d["n"] += 1
         d["bytes"] += val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
