@@ -435,9 +435,9 @@ class SingleGPU:
         self.model.zero_grad(set_to_none=True)
         out_e, out_r, _ = self.model(None, self.batch, graph or self.graph, None)
         # <out_entity, G_e> + <out_relation, G_r>   as two dot products
-        loss = torch.dot(out_e.reshape(-1), self.g_ent.reshape(-1)) + torch.dot(out_r.reshape(-1), self.g_rel.reshape(-1))
-        loss.backward()
-        return loss
+        # (the library's deterministic reduction for the value; the backward is seeded with G_e / G_r, which is d loss / d out)
+        from recon_b200 import functional as SF
+        return SF.linear_loss_backward((out_e, out_r), (self.g_ent, self.g_rel))
 
     @property
     def host(self):

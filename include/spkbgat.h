@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* spk_stream_t;              /* cudaStream_t */
 
-#define SPK_ABI_VERSION 4
+#define SPK_ABI_VERSION 5
 int spk_abi_version(void);
 const char* spk_last_error(void);
 int64_t spk_launch_count(void);          /* kernels launched through this library so far */
@@ -192,8 +192,16 @@ typedef struct {
     float* dP3; int64_t ldd3;                    /* [n_rel, width] */
     int32_t n_rel; int32_t phases;
     spk_hub_tasks rel_hub;                       /* relation segments as tasks; partial [n_tasks, ldpart >= width] */
-    float* colsum; int64_t ld_colsum;            /* optional [n_cols, ld_colsum >= n_heads] destination of phase 4 */
+    float* colsum; int64_t ld_colsum;            /* optional [n_cols, ld_colsum >= n_heads] destination of phase 8 */
+    float* rowsum; int64_t ld_rowsum;            /* optional [n_rows, ld_rowsum >= n_heads] destination of the row sums (phase 4) */
+    const float* G_rel; int64_t ldg_rel;         /* rows the relation pass gathers (null: base.G) */
+    int32_t dup; int32_t reserved;               /* 1: aggregate-then-project tables (see below) */
 } spk_edge_bwd_split_args;
+/* dup = 1 runs the same column / relation passes for the aggregate-then-project layer (spk_agg_*): base.P2 = X~ and base.P3 =
+ * Rel~ (rows [v (d_pad floats) | n_heads score scalars | pad], ld >= d_pad + 4: the SAME input row serves every head), base.G =
+ * Gx and G_rel = Gr ([n_rows, n_heads * d_pad], from spk_agg_bwd_ctx), geom.d_head = the input width; phases 2 | 4 | 8 only
+ * (spk_agg_bwd_ctx is the node pass). The per-edge dot t = c + Yb . x_j + Yc . r_k is then split over the two passes that gather
+ * Gx / Gr anyway, and the row-major regather of X~[j] (spk_agg_bwd_rows' stream kernel) is not needed. */
 int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* args, spk_stream_t stream);
 
 /* ---- K2'/K3': "aggregate-then-project" variant for layer groups whose input is narrower than their projection
@@ -246,6 +254,8 @@ typedef struct {
     spk_hub_tasks hub;                           /* partial: [n_tasks, 8] */
 } spk_agg_bwd_args;
 int spk_agg_bwd_rows(const spk_agg_bwd_args* args, spk_stream_t stream);
+/* row-context kernel alone (Gx, Gr, rowout, rowsc as [n_rows, n_heads, 4] = (q1, c, dden, 0)); rec / mask / hub unused */
+int spk_agg_bwd_ctx(const spk_agg_bwd_args* args, spk_stream_t stream);
 /* dX[i,f] = rowout[i,f] + sum_h dxc[i, h*4*f_chunks + f] + sum_c dq[i,c] V[f,c]; also emits dq [n,4] = (dq2_0,dq2_1,dq1_0,dq1_1).
  * dxc is the K4 column-pass output with geometry (H, d_head = d_pad = 4*f_chunks). */
 int spk_agg_dx(const float* rowout, int64_t ldro, const float* dxc, int64_t ldc, const float* V, int64_t n_rows,
@@ -265,6 +275,12 @@ int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t
                           const float* inv_norm, float* dew, int64_t lde, float* dx2, int64_t ldx,
                           int64_t n_rows, int32_t width, spk_stream_t stream);
 int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream);
+/* out[0] (+)= <a, b> over n contiguous floats (16-byte aligned), deterministic (fixed chunking, fp64 across threads):
+ * the linear probe loss <out_entity, G_e> + <out_relation, G_r> of SURVEY.md 8d (the reference's step writes it as
+ * (out * G).sum()). workspace: spk_inner_product_workspace_bytes() bytes of device memory. */
+int64_t spk_inner_product_workspace_bytes(void);
+int spk_inner_product(const float* a, const float* b, int64_t n, void* workspace, float* out, int32_t accumulate,
+                      spk_stream_t stream);
 
 /* ---- N1: the training step right after the hot path ----
  * batch_gat_loss (GAT/main.py:344-376): `triples` int64 [T,3] = (head, relation, tail) rows, the first n_pos positive,

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f32p = C.POINTER(C.c_float)
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Geom(C.Structure):
@@ -84,7 +84,10 @@ class EdgeBwdSplitArgs(C.Structure):
                 ("dP3", C.c_void_p), ("ldd3", C.c_int64),
                 ("n_rel", C.c_int32), ("phases", C.c_int32),
                 ("rel_hub", HubTasks),
-                ("colsum", C.c_void_p), ("ld_colsum", C.c_int64)]
+                ("colsum", C.c_void_p), ("ld_colsum", C.c_int64),
+                ("rowsum", C.c_void_p), ("ld_rowsum", C.c_int64),
+                ("G_rel", C.c_void_p), ("ldg_rel", C.c_int64),
+                ("dup", C.c_int32), ("reserved", C.c_int32)]
 
 
 class AggGeom(C.Structure):
@@ -165,6 +168,7 @@ SIGNATURES = {
     "spk_agg_fwd": (_I32, [C.POINTER(AggFwdArgs), _VP]),
     "spk_agg_bwd_pre": (_I32, [_VP, _VP, _I64, _VP, _I32, _I32, _I32, _VP, _I64, _VP, _I64, _VP]),
     "spk_agg_bwd_rows": (_I32, [C.POINTER(AggBwdArgs), _VP]),
+    "spk_agg_bwd_ctx": (_I32, [C.POINTER(AggBwdArgs), _VP]),
     "spk_agg_dx": (_I32, [_VP, _I64, _VP, _I64, _VP, _I64, _I32, _I32, _I32, _VP, _I64, _VP, _VP]),
     "spk_gemm_tn_tc_supported": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _I32]),
     "spk_gemm_tn_tc_workspace_floats": (_I64, [_I64, _I32, _I32]),
@@ -182,6 +186,8 @@ SIGNATURES = {
     "spk_residual_norm_fwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
     "spk_residual_norm_bwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP]),
     "spk_mask_from_index": (_I32, [_VP, _I64, _VP, _I64, _VP]),
+    "spk_inner_product_workspace_bytes": (_I64, []),
+    "spk_inner_product": (_I32, [_VP, _VP, _I64, _VP, _VP, _I32, _VP]),
     "spk_margin_loss_partials": (_I64, [_I64]),
     "spk_margin_loss_fwd": (_I32, [_VP, _I64, _I64, _VP, _I64, _I64, _VP, _I64, _I64, _I32, C.c_float, _I32,
                                    _VP, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -6,6 +6,7 @@
 // 128-bit load per lane, eight edges in flight; every per-edge scalar (score, LeakyReLU, exp, dropout
 // multiplier, and in the backward ds) is computed lane-parallel for 32 edges at a time. No atomics: a row is
 // summed in edge order by one warp, hub rows as fixed 256-edge tasks added in task order.
+#include <stdlib.h>
 #include "spk_agg.cuh"
 #include "spk_stream.cuh"
 
@@ -387,6 +388,157 @@ agg_fwd_stream_kernel(const AggFwdArgs a) {
     if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.nanflag, 1);
 }
 
+
+// ---- register-gather forward (round 2) --------------------------------------------------------------
+// Same work as agg_fwd_stream_kernel, without the shared-memory ring. ncu's instruction mix of the ring version showed
+// 73 warp instructions per edge of which 8.5 % were FFMA: issuing two cp.async.bulk copies per edge costs an ELECT loop
+// with four R2UR each (UBLKCP takes uniform registers) plus the mbarrier bookkeeping. A gathered row here is ONE float4
+// per lane (X~[j] chunk in lanes 0-15, Rel~[k] chunk in lanes 16-31), so a plain LDG.128 per lane per edge with AG_U edges
+// in flight costs AG_U registers per lane, not the 16+ the 832-byte rows of K2 needed: the latency depth fits registers.
+constexpr int AG_U = 8;
+constexpr int AGR_WARPS = 8;
+
+template <int HT, bool HAS2, bool TASKS>
+__global__ void __launch_bounds__(AGR_WARPS * 32, 2)
+agg_fwd_reg_kernel(const AggFwdArgs a) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int H = a.g.H;
+    SegTable st;
+    st.beg = 0; st.deg = 0;
+    bool is_hub = false;
+    long row0 = 0;
+    int task_row = 0;
+    if (!TASKS) {
+        row0 = ((long)blockIdx.x * AGR_WARPS + wid) * 32;
+        const long r = row0 + lane;
+        if (r < a.n_rows) {
+            const int b = __ldg(a.segptr + r), e = __ldg(a.segptr + r + 1);
+            st.beg = b;
+            if (e - b > a.hub.hub_thresh) is_hub = true; else st.deg = e - b;
+        }
+    } else {
+        const int task = blockIdx.x * AGR_WARPS + wid;
+        if (task >= a.hub.n_tasks) return;
+        task_row = __ldg(a.hub.task_seg + task);
+        if (lane == 0) { st.beg = __ldg(a.hub.task_beg + task); st.deg = __ldg(a.hub.task_end + task) - st.beg; }
+    }
+    st.pre = warp_excl_scan(st.deg, lane, st.total);
+    const int T = st.total;
+    const int qx = a.g.Fx4 * 4, qr = a.g.Fr4 * 4;
+    const bool has_mask = a.mask != nullptr;
+
+    float q1r[HT];
+    {
+        float4 xs = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (TASKS) xs = ldg4(a.Xrow + (long)task_row * a.ldxr + qx);
+        else if (st.deg > 0) xs = ldg4(a.Xrow + (row0 + lane) * a.ldxr + qx);
+#pragma unroll
+        for (int h = 0; h < HT; ++h) q1r[h] = f4get(xs, 2 + h);
+    }
+    if (!TASKS) {
+        unsigned empt = __ballot_sync(FULL, st.deg == 0 && !is_hub && row0 + lane < a.n_rows);
+        while (empt) { const int r = __ffs(empt) - 1; empt &= empt - 1; agg_fwd_zero_row(a, (int)(row0 + r), lane); }
+    }
+    if (T == 0) return;
+
+    AggRaw<HT> cur, nxt;
+    AggScr<HT> scur, snxt;
+    float w[HT], ee[HT];
+    bool bad = false;
+    auto compute = [&](int nb0, const AggRaw<HT>& b, const AggScr<HT>& s) {
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+            const float q1 = __shfl_sync(FULL, q1r[h], b.seg);
+            const float sc = q1 + (s.sx[h] + s.sr[h]);
+            float e = agg_exp(-(sc > 0.f ? sc : a.alpha * sc));                  // layers.py:143-146
+            if (nb0 + lane >= T || h >= H) e = 0.f;
+            bad |= (e != e);
+            ee[h] = e;
+            w[h] = e * b.m[h];                                                   // layers.py:158
+        }
+    };
+    ags_load_idx<HT, HAS2>(a.col, a.t1, a.t2, a.mask, a.mask_stride, H, st, T, 0, lane, cur);
+    ags_load_scr<HT, HAS2>(a.Xcol, a.ldxc, a.Rt, a.ldr, qx, qr, T, 0, lane, cur, scur);
+    ags_load_idx<HT, HAS2>(a.col, a.t1, a.t2, a.mask, a.mask_stride, H, st, T, 32, lane, nxt);
+
+    unsigned act = TASKS ? 1u : __ballot_sync(FULL, st.deg > 0);
+    int r = __ffs(act) - 1;
+    act &= act - 1;
+    int row_end = __shfl_sync(FULL, st.pre + st.deg, r);
+    auto load_xi = [&](int seg) {
+        const long row = TASKS ? (long)task_row : row0 + seg;
+        return lane < a.g.Fx4 ? ldg4(a.Xrow + row * a.ldxr + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TASKS) xi = load_xi(r);
+
+    const int sub = lane & 15;
+    const bool isx = lane < 16;
+    const bool active = sub < (isx ? a.g.Fx4 : a.g.Fr4);
+    // this lane's table and chunk offset: X~ rows for lanes 0-15, Rel~ rows for lanes 16-31
+    const float* tab = (isx ? a.Xcol : a.Rt) + sub * 4;
+    const long ldt = isx ? a.ldxc : a.ldr;
+    AggAcc<HT> acc;
+    agg_acc_init<HT>(acc);
+
+    for (int nb = 0; nb < T; nb += 32) {
+        // score scalars of the NEXT batch are requested now and consumed after this batch's rows (one round trip hidden)
+        ags_load_scr<HT, HAS2>(a.Xcol, a.ldxc, a.Rt, a.ldr, qx, qr, T, nb + 32, lane, nxt, snxt);
+        compute(nb, cur, scur);
+        const int nvalid = T - nb < 32 ? T - nb : 32;
+        for (int u0 = 0; u0 < nvalid; u0 += AG_U) {
+            float4 v[AG_U];
+#pragma unroll
+            for (int k = 0; k < AG_U; ++k) {
+                const int src = u0 + k;
+                const int j = __shfl_sync(FULL, cur.col, src & 31), k1 = __shfl_sync(FULL, cur.t1, src & 31);
+                const int idx = isx ? j : k1;
+                v[k] = (src < nvalid && active) ? ldg4(tab + (long)idx * ldt) : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (HAS2) {
+                    const int k2 = __shfl_sync(FULL, cur.t2, src & 31);
+                    if (src < nvalid && active && !isx && k2 >= 0) v[k] = f4add(v[k], ldg4(tab + (long)k2 * ldt));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < AG_U; ++k) {
+                const int src = u0 + k;
+                if (src >= nvalid) break;
+                const int n = nb + src;
+#pragma unroll
+                for (int h = 0; h < HT; ++h) {
+                    const float wh = __shfl_sync(FULL, w[h], src);
+                    f4fma(acc.acc[h], wh, v[k]);
+                    acc.sw[h] += wh;
+                    acc.den[h] += has_mask ? __shfl_sync(FULL, ee[h], src) : wh;
+                }
+                if (!TASKS && n + 1 == row_end) {
+                    agg_fwd_finalize<HT>(a, (int)(row0 + r), lane, acc, xi, bad);
+                    agg_acc_init<HT>(acc);
+                    if (act) {
+                        r = __ffs(act) - 1;
+                        act &= act - 1;
+                        row_end = __shfl_sync(FULL, st.pre + st.deg, r);
+                        xi = load_xi(r);
+                    }
+                }
+            }
+        }
+        cur = nxt; scur = snxt;
+        ags_load_idx<HT, HAS2>(a.col, a.t1, a.t2, a.mask, a.mask_stride, H, st, T, nb + 64, lane, nxt);
+    }
+    if (TASKS) {
+        const int task = blockIdx.x * AGR_WARPS + wid;
+        float* part = a.hub.partial + (long)task * a.hub.ldpart;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) st4(part + h * 128 + lane * 4, h < HT ? acc.acc[h < HT ? h : 0] : make_float4(0.f, 0.f, 0.f, 0.f));
+        if (lane < 4) {
+            part[256 + lane] = lane < HT ? selh<HT>(lane, acc.den) : 0.f;
+            part[260 + lane] = lane < HT ? selh<HT>(lane, acc.sw) : 0.f;
+        }
+    }
+    if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.nanflag, 1);
+}
+
 // one CTA per hub row: partials added in the fixed order of cta_sum_partials, then the row epilogue
 template <int HT>
 __global__ void __launch_bounds__(1024)
@@ -412,8 +564,29 @@ agg_fwd_hub_finalize_kernel(const AggFwdArgs a) {
     if (__any_sync(FULL, bad) && lane == 0) atomicOr(a.nanflag, 1);
 }
 
+// SPK_AGG_FWD=ring selects the shared-memory ring kernels (round 1); default: register gathers
+static bool agg_fwd_ring() {
+    const char* e = getenv("SPK_AGG_FWD");
+    return e && e[0] == 'r';
+}
+
 template <int HT, bool HAS2>
 int launch_agg_fwd_t(const AggFwdArgs& a, cudaStream_t s) {
+    if (!agg_fwd_ring()) {
+        if (a.n_rows > 0) {
+            const unsigned grid = (unsigned)((a.n_rows + 32L * AGR_WARPS - 1) / (32L * AGR_WARPS));
+            agg_fwd_reg_kernel<HT, HAS2, false><<<grid, AGR_WARPS * 32, 0, s>>>(a);
+            if (int rc = check_launch("agg_fwd_reg_rows")) return rc;
+        }
+        if (a.hub.n_tasks > 0) {
+            const unsigned grid = (a.hub.n_tasks + AGR_WARPS - 1) / AGR_WARPS;
+            agg_fwd_reg_kernel<HT, HAS2, true><<<grid, AGR_WARPS * 32, 0, s>>>(a);
+            if (int rc = check_launch("agg_fwd_reg_tasks")) return rc;
+            agg_fwd_hub_finalize_kernel<HT><<<a.hub.n_hubs, 1024, 0, s>>>(a);
+            if (int rc = check_launch("agg_fwd_hub_finalize")) return rc;
+        }
+        return 0;
+    }
     constexpr int G = 4, NG = HAS2 ? 3 : 4;
     const uint32_t rbx = (uint32_t)(a.g.Fx4 + 1) * 16u, rbr = (uint32_t)(a.g.Fr4 + 1) * 16u;
     const size_t smem = (size_t)AGS_WARPS * ags_warp_bytes_c<HAS2, G, NG>(rbx, rbr);
@@ -442,6 +615,7 @@ int launch_agg_fwd_t(const AggFwdArgs& a, cudaStream_t s) {
 // Row-context kernel (one warp per row, pure streaming): from dZn, den, sw, dden, X~ it emits
 //   Gx[i] = Yb per head, Gr[i] = Yc per head (the rows the column / relation passes gather, and the per-row context of
 //   the edge kernel), rowout[i, :4*Fx4] = sum_h sw_h Ya_h, rowsc[i] = (q1_0, q1_1, c_0, c_1, dden_0, dden_1, 0, 0).
+template <bool SPLIT_LAYOUT>
 __global__ void __launch_bounds__(SPK_CTA_THREADS)
 agg_bwd_ctx_kernel(const AggBwdArgs a) {
     const int lane = threadIdx.x & 31;
@@ -487,8 +661,13 @@ agg_bwd_ctx_kernel(const AggBwdArgs a) {
     }
     if (lane < a.g.Fx4) st4(a.rowout + (long)row * a.ldro + lane * 4, dxr);
     if (lane == 0) {
-        st4(a.rowsc + (long)row * 8, make_float4(xs.z, xs.w, c[0], c[1]));
-        st4(a.rowsc + (long)row * 8 + 4, make_float4(dd[0], dd[1], 0.f, 0.f));
+        if (SPLIT_LAYOUT) {                        // [n_rows, H, 4] = (q1, c, dden, 0): what the split-dot passes read per row
+            st4(a.rowsc + (long)row * 4 * H, make_float4(xs.z, c[0], dd[0], 0.f));
+            if (H > 1) st4(a.rowsc + (long)row * 4 * H + 4, make_float4(xs.w, c[1], dd[1], 0.f));
+        } else {
+            st4(a.rowsc + (long)row * 8, make_float4(xs.z, xs.w, c[0], c[1]));
+            st4(a.rowsc + (long)row * 8 + 4, make_float4(dd[0], dd[1], 0.f, 0.f));
+        }
     }
 }
 
@@ -734,7 +913,7 @@ int launch_agg_bwd_t(const AggBwdArgs& a, cudaStream_t s) {
     const size_t smem = (size_t)AGS_WARPS * ags_warp_bytes_c<HAS2, G, NG>(rbx, rbr);
     static SmemLimit lim_rows, lim_tasks;
     if (a.n_rows > 0) {
-        agg_bwd_ctx_kernel<<<(a.n_rows + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA, SPK_CTA_THREADS, 0, s>>>(a);
+        agg_bwd_ctx_kernel<false><<<(a.n_rows + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA, SPK_CTA_THREADS, 0, s>>>(a);
         if (int rc = check_launch("agg_bwd_ctx")) return rc;
         lim_rows.ensure(agg_bwd_stream_kernel<HT, HAS2, false>, smem);
         const unsigned grid = (unsigned)((a.n_rows + 32L * AGS_WARPS - 1) / (32L * AGS_WARPS));
@@ -901,6 +1080,12 @@ int launch_agg_bwd_rows(const AggBwdArgs& a, cudaStream_t s) {
     const bool has2 = a.t2 != nullptr;
     if (a.g.H == 1) return has2 ? launch_agg_bwd_t<1, true>(a, s) : launch_agg_bwd_t<1, false>(a, s);
     return has2 ? launch_agg_bwd_t<2, true>(a, s) : launch_agg_bwd_t<2, false>(a, s);
+}
+
+int launch_agg_bwd_ctx_split(const AggBwdArgs& a, cudaStream_t s) {
+    if (a.n_rows <= 0) return 0;
+    agg_bwd_ctx_kernel<true><<<(a.n_rows + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA, SPK_CTA_THREADS, 0, s>>>(a);
+    return check_launch("agg_bwd_ctx");
 }
 
 int launch_agg_bwd_pre(const float* out, const float* dout, long ldo, const float* den, int H, int D, int apply_elu,

@@ -66,6 +66,7 @@ int launch_agg_fwd(const AggFwdArgs& a, cudaStream_t s);
 int launch_agg_bwd_pre(const float* out, const float* dout, long ldo, const float* den, int H, int D, int apply_elu,
                        float* dhn, long ldd, float* dden, long n, cudaStream_t s);
 int launch_agg_bwd_rows(const AggBwdArgs& a, cudaStream_t s);
+int launch_agg_bwd_ctx_split(const AggBwdArgs& a, cudaStream_t s);   // row-context kernel alone, rowsc as [n, H, 4]
 int launch_agg_dx(const float* rowout, long ldro, const float* dxc, long ldc, const float* V, long n, int F, int F4,
                   int H, float* dX, long lddx, float* dq, cudaStream_t s);
 int launch_elu_inplace(float* x, long ld, long n, int width, cudaStream_t s);

@@ -230,7 +230,7 @@ int spk_edge_attn_bwd_segments(const spk_seg_gather_args* p, spk_stream_t stream
     return launch_seg_gather(a, (cudaStream_t)stream);
 }
 
-static int fused_args_of(const spk_edge_bwd_fused_args* p, BwdFusedArgs& a, const char* who);
+static int fused_args_of(const spk_edge_bwd_fused_args* p, BwdFusedArgs& a, const char* who, int dup = 0);
 
 int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* p, spk_stream_t stream) {
     BwdFusedArgs a;
@@ -241,7 +241,7 @@ int spk_edge_attn_bwd_fused(const spk_edge_bwd_fused_args* p, spk_stream_t strea
 
 int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* q, spk_stream_t stream) {
     BwdSplitArgs a;
-    if (int rc = fused_args_of(&q->base, a.f, "edge_attn_bwd_split")) return rc;
+    if (int rc = fused_args_of(&q->base, a.f, "edge_attn_bwd_split", q->dup)) return rc;
     if (q->base.csc_t2 != nullptr) { set_error("edge_attn_bwd_split: graphs with 2-hop edges are not supported"); return 1; }
     if ((q->ldd3 & 3) || q->ldd3 < q->base.geom.width || !aligned16(q->dP3) || !aligned16(q->rec4) ||
         (reinterpret_cast<uintptr_t>(q->dsv) & 3)) {
@@ -261,6 +261,14 @@ int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* q, spk_stream_t strea
     }
     a.phases = q->phases == 0 ? 15 : q->phases;
     a.colsum = q->colsum; a.ld_colsum = q->ld_colsum;
+    a.rowsum = q->rowsum; a.ld_rowsum = q->ld_rowsum;
+    a.G_rel = q->G_rel ? q->G_rel : a.f.G; a.ldg_rel = q->G_rel ? q->ldg_rel : a.f.ldg;
+    a.dup = q->dup;
+    if ((a.rowsum && a.ld_rowsum < q->base.geom.n_heads) || (q->G_rel && ((q->ldg_rel & 3) || !aligned16(q->G_rel) ||
+        q->ldg_rel < q->base.geom.n_heads * q->base.geom.d_pad)) || (a.dup && (a.phases & 1))) {
+        set_error("edge_attn_bwd_split: bad rowsum / G_rel / dup arguments");
+        return 1;
+    }
     if (a.phases < 0 || a.phases > 15 || (a.colsum && a.ld_colsum < q->base.geom.n_heads)) {
         set_error("edge_attn_bwd_split: bad phases / colsum");
         return 1;
@@ -273,11 +281,12 @@ int spk_edge_attn_bwd_split(const spk_edge_bwd_split_args* q, spk_stream_t strea
     return launch_edge_bwd_split(a, (cudaStream_t)stream);
 }
 
-static int fused_args_of(const spk_edge_bwd_fused_args* p, BwdFusedArgs& a, const char* who) {
+static int fused_args_of(const spk_edge_bwd_fused_args* p, BwdFusedArgs& a, const char* who, int dup) {
     if (!geom_ok(p->geom, &a.g, who)) return 1;
+    const int64_t tab_w = dup ? p->geom.d_pad + 4 : p->geom.width;      // dup: one copy of the vector + the score scalars
     if ((p->ld1 & 3) || (p->ld2 & 3) || (p->ld3 & 3) || (p->ldg & 3) || (p->ldd1 & 3) || (p->ldd2 & 3) ||
         p->ldg < p->geom.n_heads * p->geom.d_pad || p->ldd1 < p->geom.width || p->ldd2 < p->geom.width ||
-        p->ld1 < p->geom.width || p->ld2 < p->geom.width || p->ld3 < p->geom.width ||
+        (!dup && p->ld1 < p->geom.width) || p->ld2 < tab_w || p->ld3 < tab_w ||
         !aligned16(p->P1) || !aligned16(p->P2) || !aligned16(p->P3) || !aligned16(p->G) || !aligned16(p->dP1) ||
         !aligned16(p->dP2) || !aligned16(p->rowsc)) {
         set_error("%s: bad leading dimension or alignment", who);
@@ -373,6 +382,26 @@ int spk_agg_bwd_rows(const spk_agg_bwd_args* p, spk_stream_t stream) {
     return launch_agg_bwd_rows(a, (cudaStream_t)stream);
 }
 
+int spk_agg_bwd_ctx(const spk_agg_bwd_args* p, spk_stream_t stream) {
+    AggBwdArgs a;
+    if (!agg_geom_ok(p->geom, &a.g, "agg_bwd_ctx")) return 1;
+    const int wx = 4 * a.g.Fx4 + 4;
+    if ((p->ldxr & 3) || (p->ldz & 3) || (p->ldgx & 3) || (p->ldgr & 3) || (p->ldro & 3) || p->ldxr < wx ||
+        p->ldz < (int64_t)a.g.H * a.g.LZ || p->ldgx < (int64_t)a.g.H * 4 * a.g.Fx4 || p->ldgr < (int64_t)a.g.H * 4 * a.g.Fr4 ||
+        p->ldro < wx || !aligned16(p->xrow) || !aligned16(p->dz) || !aligned16(p->gx) || !aligned16(p->gr) ||
+        !aligned16(p->rowout) || !p->rowsc || !aligned16(p->rowsc)) {
+        set_error("agg_bwd_ctx: bad leading dimension or alignment");
+        return 1;
+    }
+    a.segptr = nullptr; a.col = nullptr; a.t1 = nullptr; a.t2 = nullptr;
+    a.Xrow = p->xrow; a.ldxr = p->ldxr; a.Xcol = nullptr; a.ldxc = 0; a.Rt = nullptr; a.ldr = 0;
+    a.mask = nullptr; a.mask_stride = 0;
+    a.dZ = p->dz; a.ldz = p->ldz; a.den = p->den; a.sw = p->sw; a.dden = p->dden;
+    a.Gx = p->gx; a.ldgx = p->ldgx; a.Gr = p->gr; a.ldgr = p->ldgr; a.rowout = p->rowout; a.ldro = p->ldro; a.rowsc = p->rowsc; a.rec = nullptr;
+    a.n_rows = p->n_rows; a.alpha = p->alpha;
+    return launch_agg_bwd_ctx_split(a, (cudaStream_t)stream);
+}
+
 int spk_agg_dx(const float* rowout, int64_t ldro, const float* dxc, int64_t ldc, const float* V, int64_t n_rows, int32_t F,
                int32_t f_chunks, int32_t n_heads, float* dX, int64_t lddx, float* dq, spk_stream_t stream) {
     if (F < 1 || f_chunks != (F + 3) / 4 || n_heads < 1 || n_heads > 2 || ldro < 4 * f_chunks + 4 ||
@@ -412,6 +441,11 @@ int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t
 }
 int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream) {
     return mask_from_index(reinterpret_cast<const long long*>(idx), n_idx, mask, n_rows, (cudaStream_t)stream);
+}
+int64_t spk_inner_product_workspace_bytes(void) { return inner_product_workspace_bytes(); }
+int spk_inner_product(const float* a, const float* b, int64_t n, void* workspace, float* out, int32_t accumulate,
+                      spk_stream_t stream) {
+    return inner_product(a, b, n, workspace, out, accumulate, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -52,6 +52,10 @@ struct BwdSplitArgs {
     HubTasks rel_hub;                     // partial: [n_tasks, >= Wd]
     int phases;                           // bit 0: node pass, 1: column pass, 2: relation pass + row sums, 3: column sums
     float* colsum; long ld_colsum;        // optional destination of the column sums instead of the q slot of dP2~
+    float* rowsum; long ld_rowsum;        // optional destination of the row sums instead of the q slot of dP1~
+    const float* G_rel; long ldg_rel;     // rows gathered by the relation pass (default: G)
+    int dup;                              // aggregate-then-project tables: P2 / P3 rows are [v (Dp) | H scalars | pad] and stand
+                                          // for [v | v | ... | scalars]: the same input row under every head
 };
 
 int launch_edge_bwd_fused(const BwdFusedArgs& a, cudaStream_t s);

@@ -29,14 +29,17 @@ struct SegCtx {
 };
 
 template <int NCH, int HT>
-__device__ __forceinline__ void seg_ctx_load(const float* __restrict__ row, const LayerGeom& g, int lane, SegCtx<NCH, HT>& cc) {
+__device__ __forceinline__ void seg_ctx_load(const float* __restrict__ row, const LayerGeom& g, int lane, SegCtx<NCH, HT>& cc,
+                                             int dup = 0) {
 #pragma unroll
     for (int ci = 0; ci < NCH; ++ci) {
         const int c4 = lane + 32 * ci;
         cc.hc[ci] = (HT > 1 && c4 < g.Dt4) ? c4 / g.Dp4 : 0;
-        cc.p[ci] = c4 < g.Dt4 ? ldg4(row + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // dup: the table row holds ONE copy of the vector (Dp floats) that every head uses
+        const int src4 = dup ? c4 % g.Dp4 : c4;
+        cc.p[ci] = c4 < g.Dt4 ? ldg4(row + src4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float4 qv = ldg4(row + (long)g.Dt4 * 4);
+    const float4 qv = ldg4(row + (long)(dup ? g.Dp4 : g.Dt4) * 4);
 #pragma unroll
     for (int h = 0; h < HT; ++h) cc.q[h] = f4get(qv, h);
 }
@@ -138,7 +141,7 @@ __device__ __forceinline__ void split_cols_accumulate(const BwdSplitArgs& a, int
 #pragma unroll
         for (int h = 0; h < HT; ++h) { my_w[h] = 0.f; my_A[h] = 0.f; my_B[h] = 0.f; my_t[h] = 0.f; }
         if (lane < n) {
-            const float4 q3 = ldg4(a.P3 + (long)my_k1 * a.ld3 + (long)g.Dt4 * 4);
+            const float4 q3 = ldg4(a.P3 + (long)my_k1 * a.ld3 + (long)(a.dup ? g.Dp4 : g.Dt4) * 4);
 #pragma unroll
             for (int h = 0; h < HT; ++h) {
                 if (h < H) {
@@ -181,7 +184,7 @@ split_cols_kernel(const BwdSplitArgs a) {
     split_acc_init<NCH, HT>(st);
     if (end > beg) {
         SegCtx<NCH, HT> cc;
-        seg_ctx_load<NCH, HT>(a.P2 + (long)colj * a.ld2, a.g, lane, cc);
+        seg_ctx_load<NCH, HT>(a.P2 + (long)colj * a.ld2, a.g, lane, cc, a.dup);
         split_cols_accumulate<NCH, HT, U>(a, beg, end, lane, cc, st);
     }
     split_store<NCH, HT>(a.dP2 + (long)colj * a.ldd2, a.g, lane, st);
@@ -197,7 +200,7 @@ split_cols_tasks_kernel(const BwdSplitArgs a) {
     SplitAcc<NCH, HT> st;
     split_acc_init<NCH, HT>(st);
     SegCtx<NCH, HT> cc;
-    seg_ctx_load<NCH, HT>(a.P2 + (long)colj * a.ld2, a.g, lane, cc);
+    seg_ctx_load<NCH, HT>(a.P2 + (long)colj * a.ld2, a.g, lane, cc, a.dup);
     split_cols_accumulate<NCH, HT, U>(a, __ldg(a.col_hub.task_beg + task), __ldg(a.col_hub.task_end + task), lane, cc, st);
     split_store<NCH, HT>(a.col_hub.partial + (long)task * a.col_hub.ldpart, a.g, lane, st);
 }
@@ -216,7 +219,7 @@ __device__ __forceinline__ void split_rels_accumulate(const BwdSplitArgs& a, int
             my_pos = __ldg(a.rel_pos + base + lane);
         }
         float4 v[U][NCH];
-        gather_rows<NCH, U>(a.G, a.ldg, g.Dt4, my_row, 0, n, lane, v);
+        gather_rows<NCH, U>(a.G_rel, a.ldg_rel, g.Dt4, my_row, 0, n, lane, v);
         float my_w[HT], my_A[HT], my_B[HT], my_t[HT];
 #pragma unroll
         for (int h = 0; h < HT; ++h) { my_w[h] = 0.f; my_A[h] = 0.f; my_B[h] = 0.f; my_t[h] = 0.f; }
@@ -233,7 +236,7 @@ __device__ __forceinline__ void split_rels_accumulate(const BwdSplitArgs& a, int
             consume_rows<NCH, HT, U>(cc, v, u0, n, lane, my_w, my_t, st);
             u0 += U;
             if (u0 >= n) break;
-            gather_rows<NCH, U>(a.G, a.ldg, g.Dt4, my_row, u0, n, lane, v);
+            gather_rows<NCH, U>(a.G_rel, a.ldg_rel, g.Dt4, my_row, u0, n, lane, v);
         }
         if (lane < n) {
 #pragma unroll
@@ -260,7 +263,7 @@ split_rels_kernel(const BwdSplitArgs a) {
     split_acc_init<NCH, HT>(st);
     if (end > beg) {
         SegCtx<NCH, HT> cc;
-        seg_ctx_load<NCH, HT>(a.P3 + (long)k * a.ld3, a.g, lane, cc);
+        seg_ctx_load<NCH, HT>(a.P3 + (long)k * a.ld3, a.g, lane, cc, a.dup);
         split_rels_accumulate<NCH, HT, U>(a, beg, end, lane, cc, st);
     }
     split_store<NCH, HT>(a.dP3 + (long)k * a.ldd3, a.g, lane, st);
@@ -276,7 +279,7 @@ split_rels_tasks_kernel(const BwdSplitArgs a) {
     SplitAcc<NCH, HT> st;
     split_acc_init<NCH, HT>(st);
     SegCtx<NCH, HT> cc;
-    seg_ctx_load<NCH, HT>(a.P3 + (long)k * a.ld3, a.g, lane, cc);
+    seg_ctx_load<NCH, HT>(a.P3 + (long)k * a.ld3, a.g, lane, cc, a.dup);
     split_rels_accumulate<NCH, HT, U>(a, __ldg(a.rel_hub.task_beg + task), __ldg(a.rel_hub.task_end + task), lane, cc, st);
     split_store<NCH, HT>(a.rel_hub.partial + (long)task * a.rel_hub.ldpart, a.g, lane, st);
 }
@@ -443,8 +446,12 @@ int launch_split_t(const BwdSplitArgs& a, cudaStream_t s) {
             fa.outp = a.dP3; fa.ldout = a.ldd3; fa.n_seg = a.n_rel; fa.prefer_stream = 0; fa.g = a.g; fa.hub = a.rel_hub;
             if (int rc = launch_seg_gather_hub_finalize(fa, s)) return rc;
         }
-        // q slot of dP1~ (rows: contiguous records)
-        if (int rc = launch_sums<HT>(a.f.rowptr, nullptr, a.dsv, a.g.H, a.f.n_rows, a.f.row_hub, a.f.dP1, a.f.ldd1, a.g.Dt4 * 4, s)) return rc;
+        // q slot of dP1~ (rows: contiguous records), or the caller's separate row-sum array
+        if (a.rowsum) {
+            if (int rc = launch_sums<HT>(a.f.rowptr, nullptr, a.dsv, a.g.H, a.f.n_rows, a.f.row_hub, a.rowsum, a.ld_rowsum, 0, s)) return rc;
+        } else {
+            if (int rc = launch_sums<HT>(a.f.rowptr, nullptr, a.dsv, a.g.H, a.f.n_rows, a.f.row_hub, a.f.dP1, a.f.ldd1, a.g.Dt4 * 4, s)) return rc;
+        }
     }
     if (a.phases & 8) {
         // q slot of dP2~ (columns: records through csc_pos), or the caller's separate column-sum array

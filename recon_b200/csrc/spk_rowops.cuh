@@ -7,4 +7,6 @@ int residual_norm(const float* ew, long lde, const float* x2, long ldx, const fl
 int residual_norm_bwd(const float* g, long ldg, const float* out, long ldo, const float* mask, const float* inv_norm,
                       float* dew, long lde, float* dx2, long ldx, long n_rows, int width, cudaStream_t s);
 int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, cudaStream_t s);
+long inner_product_workspace_bytes();
+int inner_product(const float* a, const float* b, long n, void* workspace, float* out, int accumulate, cudaStream_t s);
 }  // namespace spk

@@ -520,6 +520,7 @@ class AttentionGroupFn(torch.autograd.Function):
 # ---- aggregate-then-project variant (input narrower than the projection, i.e. layer 1) ---------
 
 AGG_MODE = "auto"      # "auto": use it where it moves fewer bytes; "off": never; "force": wherever the shape is supported
+AGG_BWD_MODE = os.environ.get("SPK_AGG_BWD_MODE", "split")     # "split": split-dot column / relation passes; "rows": round-1 schedule
 AGG_MAX_HEADS = 2
 
 
@@ -680,36 +681,94 @@ class AggGroupFn(torch.autograd.Function):
         Gx = torch.empty(n, H * Fp, **f32)
         Gr = torch.empty(n, H * Rp, **f32)
         rowout = torch.empty(n, Fp + 4, **f32)
-        rec = torch.empty(max(1, graph.n_edges), 2 * H, **f32)
         a = _lib.AggBwdArgs()
-        a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
-        a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
-        a.xrow = Xt.data_ptr(); a.ldxr = Xt.stride(0); a.xcol = Xc.data_ptr(); a.ldxc = Xc.stride(0)
-        a.rel = Rt.data_ptr(); a.ldr = Rt.stride(0)
-        if ctx.mask_csr is not None:
-            a.mask = ctx.mask_csr.data_ptr(); a.mask_stride = ctx.mask_csr.stride(0)
+        a.xrow = Xt.data_ptr(); a.ldxr = Xt.stride(0)
         a.dz = dZ.data_ptr(); a.ldz = dZ.stride(0)
         a.den = den.data_ptr(); a.sw = sw.data_ptr(); a.dden = dden.data_ptr()
         a.gx = Gx.data_ptr(); a.ldgx = Gx.stride(0); a.gr = Gr.data_ptr(); a.ldgr = Gr.stride(0)
-        rowsc = torch.empty(max(1, n), 8, **f32)                # (a rank may own no rows at all)
-        a.rowout = rowout.data_ptr(); a.ldro = rowout.stride(0); a.rowsc = rowsc.data_ptr(); a.rec = rec.data_ptr()
+        a.rowout = rowout.data_ptr(); a.ldro = rowout.stride(0)
         a.n_rows = n; a.alpha = float(ctx.alpha); a.geom = geom.struct()
-        part = _hub_partial(graph.row_hubs, 8, dev)
-        graph.row_hubs.fill(a.hub, part, 8)
-        _lib.check(lib.spk_agg_bwd_rows(C.byref(a), _lib.stream_ptr()), "agg_bwd_rows")
-        del dZ
-        # column pass: dX through the gathered side, per head chunk; relation pass: dRel
         gx_geom, gr_geom = Geometry(H, Fp), Geometry(H, Rp)
         dXc = torch.empty(graph.n_cols, gx_geom.Wd, **f32)
-        seg_gather(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, Gx, Gx.stride(0), rec, gx_geom, dXc,
-                   graph.n_cols, "cols")
+        dRc = torch.empty(graph.n_rel, gr_geom.Wd, **f32)
+        split = AGG_BWD_MODE == "split" and graph.t2 is None and Fp == Rp
+        if split:
+            # split-dot schedule (round 2): the per-edge dot t = c + Yb . x_j + Yc . r_k is formed in the two passes that
+            # gather Gx[i] / Gr[i] anyway (column pass: x_j of the column in registers; relation pass: r_k in registers),
+            # exactly as in the projected layer; the row-major pass that re-gathered X~[j] per edge is gone (2 row gathers
+            # per edge in this backward instead of 3)
+            rowsc = torch.empty(max(1, n), H, 4, **f32)
+            a.rowsc = rowsc.data_ptr()
+            _lib.check(lib.spk_agg_bwd_ctx(C.byref(a), _lib.stream_ptr()), "agg_bwd_ctx")
+            del dZ
+            ne = max(1, graph.n_edges)
+            q = _lib.EdgeBwdSplitArgs()
+            b = q.base
+            b.rowptr = graph.rowptr.data_ptr()
+            b.colptr = graph.colptr.data_ptr(); b.csc_row = graph.csc_row.data_ptr(); b.csc_pos = graph.csc_pos.data_ptr()
+            b.csc_t1 = graph.csc_t1.data_ptr()
+            b.P1 = Xc.data_ptr(); b.ld1 = Xc.stride(0)                      # (unused: the node pass is spk_agg_bwd_ctx)
+            b.P2 = Xc.data_ptr(); b.ld2 = Xc.stride(0); b.P3 = Rt.data_ptr(); b.ld3 = Rt.stride(0)
+            if ctx.mask_csr is not None:
+                b.mask = ctx.mask_csr.data_ptr(); b.mask_stride = ctx.mask_csr.stride(0)
+            b.G = Gx.data_ptr(); b.ldg = Gx.stride(0); b.rowsc = rowsc.data_ptr()
+            b.dP1 = dXc.data_ptr(); b.ldd1 = dXc.stride(0)                  # (unused: the row sums go to `rowsum`)
+            b.dP2 = dXc.data_ptr(); b.ldd2 = dXc.stride(0)
+            b.n_rows = n; b.n_cols = graph.n_cols; b.apply_elu = 0; b.alpha = float(ctx.alpha)
+            b.geom = gx_geom.struct()
+            graph.row_hubs.fill(b.row_hub, None, 0)
+            partc = _hub_partial(graph.col_hubs, gx_geom.Wd, dev)
+            graph.col_hubs.fill(b.col_hub, partc, gx_geom.Wd)
+            q.relptr = graph.relptr.data_ptr(); q.rel_row = graph.rel_row.data_ptr(); q.rel_pos = graph.rel_pos.data_ptr()
+            rec4 = torch.empty(ne, H, 4, **f32); dsv = torch.empty(ne, H, **f32)
+            q.rec4 = rec4.data_ptr(); q.dsv = dsv.data_ptr()
+            q.dP3 = dRc.data_ptr(); q.ldd3 = dRc.stride(0); q.n_rel = graph.n_rel
+            part3 = _hub_partial(graph.rel_hubs, gr_geom.Wd, dev)
+            graph.rel_hubs.fill(q.rel_hub, part3, gr_geom.Wd)
+            part1 = _hub_partial(graph.row_hubs, 4, dev)
+            graph.row_hubs.fill(q.base.row_hub, part1, 4)
+            rowsum = torch.empty(max(1, n), H, **f32)
+            q.rowsum = rowsum.data_ptr(); q.ld_rowsum = H
+            q.G_rel = Gr.data_ptr(); q.ldg_rel = Gr.stride(0)
+            q.dup = 1
+
+            def run(phases, tag):
+                q.phases = phases
+                _lib.current_tag = tag + f":w{gx_geom.Wd}"
+                try:
+                    _lib.check(lib.spk_edge_attn_bwd_split(C.byref(q), _lib.stream_ptr()), "edge_attn_bwd_split")
+                finally:
+                    _lib.current_tag = ""
+        else:
+            rec = torch.empty(max(1, graph.n_edges), 2 * H, **f32)
+            a.segptr = graph.rowptr.data_ptr(); a.col = graph.col.data_ptr(); a.t1 = graph.t1.data_ptr()
+            a.t2 = graph.t2.data_ptr() if graph.t2 is not None else None
+            a.xcol = Xc.data_ptr(); a.ldxc = Xc.stride(0)
+            a.rel = Rt.data_ptr(); a.ldr = Rt.stride(0)
+            if ctx.mask_csr is not None:
+                a.mask = ctx.mask_csr.data_ptr(); a.mask_stride = ctx.mask_csr.stride(0)
+            rowsc = torch.empty(max(1, n), 8, **f32)                # (a rank may own no rows at all)
+            a.rowsc = rowsc.data_ptr(); a.rec = rec.data_ptr()
+            part = _hub_partial(graph.row_hubs, 8, dev)
+            graph.row_hubs.fill(a.hub, part, 8)
+            _lib.check(lib.spk_agg_bwd_rows(C.byref(a), _lib.stream_ptr()), "agg_bwd_rows")
+            del dZ
+        # column pass: dX through the gathered side, per head chunk; relation pass: dRel
+        if split:
+            run(2, "cols")
+        else:
+            seg_gather(graph.colptr, graph.csc_row, graph.csc_pos, graph.col_hubs, Gx, Gx.stride(0), rec, gx_geom, dXc,
+                       graph.n_cols, "cols")
         if dist is not None:                              # partial sums over this rank's edges -> owners: the reduce-
             dXc_all = dXc                                 # scatter runs under the relation pass
             dXc_pad = torch.empty(dist.part.max_rows, gx_geom.Wd, **f32)
             hx = dist.reduce_scatter_start(dXc_all, dXc_pad)
-        dRc = torch.empty(graph.n_rel, gr_geom.Wd, **f32)
-        seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, Gr, Gr.stride(0), rec, gr_geom, dRc,
-                   graph.n_rel, "rels")
+        if split:
+            run(4, "rels")                                # relation pass + row sums of ds
+            rowout[:, Fp:Fp + H] = rowsum[:n]             # dq1 = sum of ds over the row
+        else:
+            seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, Gr, Gr.stride(0), rec, gr_geom, dRc,
+                       graph.n_rel, "rels")
         if dist is not None:
             dist.all_reduce(dRc)
             dist.all_reduce(dWa)
@@ -835,3 +894,47 @@ class ResidualNormFn(torch.autograd.Function):
                                                      _lib.ptr(dx2), dx2.stride(0), n, w, _lib.stream_ptr()),
                    "residual_norm_bwd")
         return dew, dx2, None
+
+
+# ---- linear probe loss (loss = <out_entity, G_e> + <out_relation, G_r>) ---------------------------------
+
+class InnerProductFn(torch.autograd.Function):
+    """sum_k <a_k, b_k> as a 0-dim tensor on the library's deterministic reduction (no library dot on the path)."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        k = len(tensors) // 2
+        a_list = [t.contiguous() for t in tensors[:k]]
+        b_list = [t.contiguous() for t in tensors[k:]]
+        lib = _lib.load()
+        dev = a_list[0].device
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.spk_inner_product_workspace_bytes(), dtype=torch.uint8, device=dev)
+        for i, (a, b) in enumerate(zip(a_list, b_list)):
+            assert a.shape == b.shape and a.dtype == b.dtype == torch.float32
+            _lib.check(lib.spk_inner_product(_lib.ptr(a), _lib.ptr(b), a.numel(), _lib.ptr(ws), _lib.ptr(out), int(i > 0),
+                                             _lib.stream_ptr()), "inner_product")
+        ctx.save_for_backward(*a_list, *b_list)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        t = ctx.saved_tensors
+        k = len(t) // 2
+        grads = [g * t[k + i] if ctx.needs_input_grad[i] else None for i in range(k)]
+        grads += [g * t[i] if ctx.needs_input_grad[k + i] else None for i in range(k)]
+        return tuple(grads)
+
+
+def inner_product(a_list, b_list):
+    """sum_k <a_list[k], b_list[k]> (differentiable)."""
+    return InnerProductFn.apply(*a_list, *b_list)
+
+
+def linear_loss_backward(outs, grads):
+    """loss = sum_k <outs[k], grads[k]> and its backward pass. d loss / d outs[k] IS grads[k], so the backward is seeded with
+    the G tensors directly (what loss.backward() computes after multiplying them by 1.0); returns the detached loss."""
+    with torch.no_grad():
+        loss = inner_product([o.detach() for o in outs], list(grads))
+    torch.autograd.backward(list(outs), [g.to(o.dtype) for o, g in zip(outs, grads)])
+    return loss

@@ -522,3 +522,38 @@ def test_host_staged_edges_give_the_same_layouts(n_nhop):
     bad_t = etype.clone(); bad_t[7] = -1
     with pytest.raises(IndexError):
         KGraph(edge, bad_t, nh, n, r, device=dev())
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 4096, 1_000_003, 40_000_000])
+def test_inner_product_deterministic(n):
+    """spk_inner_product: the linear probe loss <out, G>, fixed-order reduction."""
+    from recon_b200 import functional as SF
+    g = torch.Generator().manual_seed(n + 5)
+    a = torch.randn(n, generator=g); b = torch.randn(n, generator=g)
+    ad, bd = a.to(dev()), b.to(dev())
+    v = SF.inner_product([ad], [bd])
+    ref = float((a.double() * b.double()).sum())
+    scale = float((a.double() * b.double()).abs().sum()) + 1e-30
+    assert abs(float(v) - ref) / scale < 1e-6
+    assert float(SF.inner_product([ad], [bd])) == float(v)          # bit-stable
+    two = SF.inner_product([ad, ad], [bd, bd])
+    assert abs(float(two) - 2 * ref) / scale < 2e-6
+
+
+def test_linear_loss_backward_matches_autograd():
+    from recon_b200 import functional as SF
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1000, 40, generator=g).to(dev()).requires_grad_(True)
+    y = torch.randn(7, 40, generator=g).to(dev()).requires_grad_(True)
+    ge, gr = torch.randn(1000, 40, generator=g).to(dev()), torch.randn(7, 40, generator=g).to(dev())
+    loss = SF.linear_loss_backward((x * 2.0, y * 3.0), (ge, gr))
+    gx, gy = x.grad.clone(), y.grad.clone()
+    x.grad = y.grad = None
+    ref = ((x * 2.0) * ge).sum() + ((y * 3.0) * gr).sum()
+    ref.backward()
+    assert torch.equal(gx, x.grad) and torch.equal(gy, y.grad)
+    assert abs(float(loss) - float(ref)) < 1e-3 * abs(float(ref)) + 1e-3
+    # differentiable form
+    x.grad = None
+    SF.inner_product([x * 2.0], [ge]).backward()
+    assert torch.allclose(x.grad, 2.0 * ge)
