@@ -23,7 +23,7 @@ extern "C" {
 
 typedef void* spk_stream_t;              /* cudaStream_t */
 
-#define SPK_ABI_VERSION 5
+#define SPK_ABI_VERSION 6
 int spk_abi_version(void);
 const char* spk_last_error(void);
 int64_t spk_launch_count(void);          /* kernels launched through this library so far */
@@ -36,7 +36,11 @@ typedef struct {
 } spk_geom;
 
 /* Segments longer than hub_thresh are processed as chunks (tasks) with partials summed in task
- * order: deterministic handling of power-law hub rows. n_tasks == 0 disables it. */
+ * order: deterministic handling of power-law hub rows. n_tasks == 0 disables it.
+ * task_order (optional, a permutation of [0, n_tasks)): launch slot s runs task task_order[s]; the partial of a task stays
+ * at its task index, so the summation order (and every result bit) is independent of it. The relation pass uses it to run
+ * the tasks of ALL relations in ascending order of their first aggregation row: the rows gathered by concurrently running
+ * tasks then fall into one sliding window that stays L2-resident instead of each relation sweeping the whole table. */
 typedef struct {
     const int32_t* task_seg;
     const int32_t* task_beg;
@@ -49,6 +53,7 @@ typedef struct {
     int32_t n_hubs;
     int32_t hub_thresh;
     int32_t reserved;
+    const int32_t* task_order; /* [n_tasks] or null */
 } spk_hub_tasks;
 
 /* ---- K0: edge construction (replaces the Python/ATen edge prep of GAT/models.py:141-148,

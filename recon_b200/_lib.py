@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f32p = C.POINTER(C.c_float)
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class Geom(C.Structure):
@@ -26,7 +26,8 @@ class HubTasks(C.Structure):
     _fields_ = [("task_seg", C.c_void_p), ("task_beg", C.c_void_p), ("task_end", C.c_void_p),
                 ("hub_seg", C.c_void_p), ("hub_task_ptr", C.c_void_p),
                 ("partial", C.c_void_p), ("ldpart", C.c_int64),
-                ("n_tasks", C.c_int32), ("n_hubs", C.c_int32), ("hub_thresh", C.c_int32), ("reserved", C.c_int32)]
+                ("n_tasks", C.c_int32), ("n_hubs", C.c_int32), ("hub_thresh", C.c_int32), ("reserved", C.c_int32),
+                ("task_order", C.c_void_p)]
 
 
 class EdgeFwdArgs(C.Structure):

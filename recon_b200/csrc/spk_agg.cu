@@ -671,27 +671,6 @@ agg_bwd_ctx_kernel(const AggBwdArgs a) {
     }
 }
 
-// Sum each of the N per-lane values over the 32 lanes with N (not 5N) shuffles: at every stage a lane keeps half
-// of its values and hands the other half to its partner. Lane L ends with the total of value (L * N) >> 5.
-template <int N>
-__device__ __forceinline__ float transposed_warp_sum(float (&p)[N], int lane) {
-    int off = 16;
-#pragma unroll
-    for (int n = N; n > 1; n >>= 1, off >>= 1) {
-        const bool up = (lane & off) != 0;
-        const int half = n >> 1;
-#pragma unroll
-        for (int k = 0; k < half; ++k) {
-            const float keep = up ? p[k + half] : p[k];
-            const float send = up ? p[k] : p[k + half];
-            p[k] = keep + __shfl_xor_sync(FULL, send, off);
-        }
-    }
-    float r = p[0];
-    for (; off > 0; off >>= 1) r += __shfl_xor_sync(FULL, r, off);
-    return r;
-}
-
 template <int HT, bool HAS2, bool TASKS>
 __global__ void __launch_bounds__(AGS_WARPS * 32, 2)
 agg_bwd_stream_kernel(const AggBwdArgs a) {

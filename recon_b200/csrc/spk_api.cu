@@ -49,6 +49,7 @@ static HubTasks hub_of(const spk_hub_tasks& h) {
     t.partial = h.partial; t.ldpart = h.ldpart;
     t.n_tasks = h.n_tasks; t.n_hubs = h.n_hubs;
     t.hub_thresh = h.n_tasks > 0 ? h.hub_thresh : 0x7fffffff;
+    t.task_order = h.n_tasks > 0 ? h.task_order : nullptr;
     return t;
 }
 

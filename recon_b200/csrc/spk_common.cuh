@@ -35,6 +35,27 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sum each of the N per-lane values over the 32 lanes with N (not 5N) shuffles: at every stage a lane keeps half
+// of its values and hands the other half to its partner. Lane L ends with the total of value (L * N) >> 5.
+template <int N>
+__device__ __forceinline__ float transposed_warp_sum(float (&p)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, off >>= 1) {
+        const bool up = (lane & off) != 0;
+        const int half = n >> 1;
+#pragma unroll
+        for (int k = 0; k < half; ++k) {
+            const float keep = up ? p[k + half] : p[k];
+            const float send = up ? p[k] : p[k + half];
+            p[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    float r = p[0];
+    for (; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+    return r;
+}
+
 // log1p(x) on (-1, 0] as log(u) * x / (u - 1), u = fl(1 + x): the rounding of u cancels to first order (|rel err| ~ 2e-7)
 __device__ __forceinline__ float fast_log1p(float x) {
     const float u = 1.0f + x;

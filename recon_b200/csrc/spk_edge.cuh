@@ -18,7 +18,12 @@ struct HubTasks {
     int n_tasks;
     int n_hubs;
     int hub_thresh;
+    const int* task_order;    // [n_tasks] launch slot -> task (null: identity); partials stay indexed by task
 };
+
+__device__ __forceinline__ int hub_task_of_slot(const HubTasks& h, int slot) {
+    return h.task_order ? __ldg(h.task_order + slot) : slot;
+}
 
 struct EdgeFwdArgs {
     const int* segptr;        // [n_rows+1] CSR keyed on edge[0]

@@ -323,8 +323,9 @@ template <int NCH, int U, int MINB>
 __global__ void __launch_bounds__(SPK_CTA_THREADS, MINB)
 seg_gather_tasks_kernel(const SegGatherArgs a) {
     const int lane = threadIdx.x & 31;
-    const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (task >= a.hub.n_tasks) return;
+    const int slot = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (slot >= a.hub.n_tasks) return;
+    const int task = hub_task_of_slot(a.hub, slot);
     int hc[NCH];
     SegAcc<NCH> st;
     seg_init<NCH>(a.g, lane, hc, st);

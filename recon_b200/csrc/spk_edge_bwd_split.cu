@@ -92,6 +92,8 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ G, long ld
 }
 
 // dot of every gathered row with the segment context per head -> my_t of the lane that owns the edge; acc += w * row
+// (reducing the U * HT partial dots together with transposed_warp_sum was measured: no gain on the 26-float4 rows of layer 1,
+// 8 % slower on the 50-float4 rows of layer 2 -- these passes wait on the gathers, not on the shuffles)
 template <int NCH, int HT, int U>
 __device__ __forceinline__ void consume_rows(const SegCtx<NCH, HT>& cc, const float4 (&v)[U][NCH], int u0, int n, int lane,
                                              const float (&my_w)[HT], float (&my_t)[HT], SplitAcc<NCH, HT>& st) {
@@ -273,8 +275,9 @@ template <int NCH, int HT, int U, int MINB>
 __global__ void __launch_bounds__(SPK_CTA_THREADS, MINB)
 split_rels_tasks_kernel(const BwdSplitArgs a) {
     const int lane = threadIdx.x & 31;
-    const int task = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (task >= a.rel_hub.n_tasks) return;
+    const int slot = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (slot >= a.rel_hub.n_tasks) return;
+    const int task = hub_task_of_slot(a.rel_hub, slot);      // row-window order: concurrently running tasks share G rows in L2
     const int k = __ldg(a.rel_hub.task_seg + task);
     SplitAcc<NCH, HT> st;
     split_acc_init<NCH, HT>(st);

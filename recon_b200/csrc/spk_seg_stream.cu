@@ -53,7 +53,7 @@ seg_gather_stream_kernel(const SegGatherArgs a) {
             if (e - b > a.hub.hub_thresh) is_hub = true; else st.deg = e - b;
         }
     } else {
-        const int task = blockIdx.x * SS_WARPS + wid;
+        const int task = blockIdx.x * SS_WARPS + wid;            // (opt-in kernel: hub.task_order is not used here)
         if (task >= a.hub.n_tasks) return;
         if (lane == 0) { st.beg = __ldg(a.hub.task_beg + task); st.deg = __ldg(a.hub.task_end + task) - st.beg; }
     }

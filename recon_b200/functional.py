@@ -766,6 +766,15 @@ class AggGroupFn(torch.autograd.Function):
         if split:
             run(4, "rels")                                # relation pass + row sums of ds
             rowout[:, Fp:Fp + H] = rowsum[:n]             # dq1 = sum of ds over the row
+            # dq2 = sum of ds over the column (needs the relation pass): straight into the q slot of dXc on one GPU; with
+            # the partial dXc already on its way to the owners, into a separate [n_cols, H] array reduce-scattered on its own
+            if dist is not None:
+                colsum = torch.empty(graph.n_cols, H, **f32)
+                q.colsum = colsum.data_ptr(); q.ld_colsum = H
+            run(8, "colsums")
+            if dist is not None:
+                qs_pad = torch.empty(dist.part.max_rows, H, **f32)
+                hq = dist.reduce_scatter_start(colsum, qs_pad)
         else:
             seg_gather(graph.relptr, graph.rel_row, graph.rel_pos, graph.rel_hubs, Gr, Gr.stride(0), rec, gr_geom, dRc,
                        graph.n_rel, "rels")
@@ -778,6 +787,9 @@ class AggGroupFn(torch.autograd.Function):
             hx.wait()
             dXc = dXc_pad[:n_loc]
             del dXc_all
+            if split:
+                hq.wait()
+                dXc[:, H * Fp:H * Fp + H].copy_(qs_pad[:n_loc])
         n = n_loc
         dX = torch.empty(n, geom.F, **f32)
         dq = torch.empty(n, 4, **f32)

@@ -9,6 +9,7 @@ All integer work runs in libspkbgat (spk_edges_concat, spk_sort_pairs, spk_segme
 used for allocation and for the O(#hubs) task tables only.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -17,16 +18,23 @@ from . import _lib
 HUB_THRESH = 512      # segments longer than this are split ...
 HUB_CHUNK = 256       # ... into tasks of this many edges
 HUB_MAX_TASKS = 4096  # ... but never more tasks than this per segment (longer tasks instead; long tasks are a tail, keep it high)
+# relation segments (E / R edges each, sorted by aggregation row inside a relation): short tasks launched in ascending order
+# of their first row, so the G rows gathered by the tasks in flight form one sliding window that fits in L2
+REL_CHUNK = int(os.environ.get("SPK_REL_CHUNK", "64"))
+REL_WINDOW_ORDER = os.environ.get("SPK_REL_ORDER", "1") != "0"
 
 
 class HubSet:
     """Task table for the segments of one ordering that exceed HUB_THRESH (see spk_hub_tasks)."""
 
-    def __init__(self, ptr, thresh=HUB_THRESH, chunk=HUB_CHUNK):
+    def __init__(self, ptr, thresh=HUB_THRESH, chunk=HUB_CHUNK, order_by=None, order_bits=31):
+        """order_by: optional per-entry int32 key array (e.g. the aggregation row of every entry, ascending inside a
+        segment); tasks are then LAUNCHED in ascending order of the key of their first entry (task_order), while partials
+        and their summation order stay in task order."""
         self.thresh = thresh
         self.n_tasks = 0
         self.n_hubs = 0
-        self.task_seg = self.task_beg = self.task_end = self.hub_seg = self.hub_task_ptr = None
+        self.task_seg = self.task_beg = self.task_end = self.hub_seg = self.hub_task_ptr = self.task_order = None
         if ptr.numel() <= 1:
             return
         ptr64 = ptr.long()
@@ -53,6 +61,9 @@ class HubSet:
         self.task_end = end.int().contiguous()
         self.hub_seg = hub_seg.int().contiguous()
         self.hub_task_ptr = tptr.int().contiguous()
+        if order_by is not None and self.n_tasks > 1:
+            key = _gather(order_by, self.task_beg)
+            _, self.task_order = sort_pairs(key, _iota(self.n_tasks, ptr.device), order_bits)
 
     def fill(self, hub, partial, ldpart):
         """Populate a _lib.HubTasks struct; `partial` is the per-call scratch tensor (or None)."""
@@ -64,6 +75,7 @@ class HubSet:
             hub.task_end = self.task_end.data_ptr(); hub.hub_seg = self.hub_seg.data_ptr()
             hub.hub_task_ptr = self.hub_task_ptr.data_ptr()
             hub.partial = partial.data_ptr() if partial is not None else None; hub.ldpart = ldpart
+            hub.task_order = self.task_order.data_ptr() if self.task_order is not None else None
 
 
 def triples_to_adj(triples, is_unweigted=False, directed=True):
@@ -278,7 +290,10 @@ class KGraph:
         self.relptr = _segment_ptr(rkeys, self.n_rel)
         self.rel_pos = rpos
         self.rel_row = _gather(self.row, rpos)
-        self.rel_hubs = HubSet(self.relptr)
+        if REL_WINDOW_ORDER:
+            self.rel_hubs = HubSet(self.relptr, chunk=REL_CHUNK, order_by=self.rel_row, order_bits=_key_bits(self.n_nodes))
+        else:
+            self.rel_hubs = HubSet(self.relptr)
 
     def to_csr_order(self, per_edge):
         """Reorder a per-edge tensor given in the caller's edge order ([..., E]) into CSR order."""

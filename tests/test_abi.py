@@ -34,7 +34,7 @@ def test_struct_sizes_match_header_layout():
     import ctypes as C
     from recon_b200 import _lib
     assert C.sizeof(_lib.Geom) == 16
-    assert C.sizeof(_lib.HubTasks) == 5 * 8 + 8 + 8 + 16
+    assert C.sizeof(_lib.HubTasks) == 5 * 8 + 8 + 8 + 16 + 8        # + task_order (ABI 6)
     assert C.sizeof(_lib.EdgeFwdArgs) == 17 * 8 + 16 + C.sizeof(_lib.Geom) + C.sizeof(_lib.HubTasks)
     assert C.sizeof(_lib.EdgeBwdRowsArgs) == 21 * 8 + 16 + C.sizeof(_lib.Geom) + C.sizeof(_lib.HubTasks)
     assert C.sizeof(_lib.SegGatherArgs) == 8 * 8 + 8 + C.sizeof(_lib.Geom) + C.sizeof(_lib.HubTasks)
