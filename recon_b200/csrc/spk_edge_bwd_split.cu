@@ -290,27 +290,42 @@ split_rels_tasks_kernel(const BwdSplitArgs a) {
 // ---- sums of ds ------------------------------------------------------------------------------------
 // dst[seg, qoff + h] = sum over the segment's entries e of dsv[idx(e), h]; idx = identity (rows: records are contiguous)
 // or csc_pos (columns). Warp per segment, lane-strided in ascending order + butterfly: fixed summation order.
+// SUM_G lanes per segment (segments average ~10 entries: a whole warp per segment spent its time on two dependent round
+// trips and a butterfly for 10 numbers; 2M warps of that cost 0.4-0.5 ms per launch, four launches per step)
+constexpr int SUM_G = 4;
 template <int HT>
 __global__ void __launch_bounds__(SPK_CTA_THREADS)
 split_sum_kernel(const int* __restrict__ segptr, const int* __restrict__ idx, const float* __restrict__ dsv, int H, int n_seg,
                  int hub_thresh, float* __restrict__ dst, long ldd, int qoff) {
-    const int lane = threadIdx.x & 31;
-    const int seg = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (seg >= n_seg) return;
-    const int beg = __ldg(segptr + seg), end = __ldg(segptr + seg + 1);
-    if (end - beg > hub_thresh) return;
+    const int sub = threadIdx.x % SUM_G;
+    const long seg_l = ((long)blockIdx.x * SPK_CTA_THREADS + threadIdx.x) / SUM_G;
+    const bool live = seg_l < n_seg;
+    const int seg = live ? (int)seg_l : n_seg - 1;
+    const int beg = __ldg(segptr + seg);
+    int end = __ldg(segptr + seg + 1);
+    const bool skip = !live || end - beg > hub_thresh;
+    if (skip) end = beg;
     float u[HT];
 #pragma unroll
     for (int h = 0; h < HT; ++h) u[h] = 0.f;
-    for (int e = beg + lane; e < end; e += 32) {
+#pragma unroll 2
+    for (int e = beg + sub; e < end; e += SUM_G) {
         const long p = idx ? (long)__ldg(idx + e) : (long)e;
+        if (HT == 2 && H == 2) {
+            const float2 d = __ldg(reinterpret_cast<const float2*>(dsv) + p);
+            u[0] += d.x; u[HT > 1 ? 1 : 0] += d.y;
+        } else {
 #pragma unroll
-        for (int h = 0; h < HT; ++h)
-            if (h < H) u[h] += __ldg(dsv + p * H + h);
+            for (int h = 0; h < HT; ++h)
+                if (h < H) u[h] += __ldg(dsv + p * H + h);
+        }
     }
 #pragma unroll
-    for (int h = 0; h < HT; ++h) u[h] = warp_sum(u[h]);
-    if (lane < H) dst[(long)seg * ldd + qoff + lane] = selh<HT>(lane, u);
+    for (int h = 0; h < HT; ++h) {
+#pragma unroll
+        for (int o = SUM_G / 2; o > 0; o >>= 1) u[h] += __shfl_xor_sync(0xffffffffu, u[h], o);
+    }
+    if (!skip && sub < H) dst[(long)seg * ldd + qoff + sub] = selh<HT>(sub, u);
 }
 
 // hub segments: one warp per 256-entry task (the hub task table of the segment ordering) writes a partial, then one CTA per
@@ -366,7 +381,8 @@ template <int HT>
 int launch_sums(const int* segptr, const int* idx, const float* dsv, int H, int n_seg, const HubTasks& hub, float* dst,
                 long ldd, int qoff, cudaStream_t s) {
     if (n_seg <= 0) return 0;
-    const unsigned grid = (n_seg + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+    static_assert(HT <= SUM_G, "a segment's lanes store one head each");
+    const unsigned grid = (unsigned)(((long)n_seg * SUM_G + SPK_CTA_THREADS - 1) / SPK_CTA_THREADS);
     split_sum_kernel<HT><<<grid, SPK_CTA_THREADS, 0, s>>>(segptr, idx, dsv, H, n_seg, hub.hub_thresh, dst, ldd, qoff);
     if (int rc = check_launch("split_sum")) return rc;
     if (hub.n_tasks > 0) {
@@ -413,9 +429,26 @@ int launch_split_passes(const BwdSplitArgs& a, cudaStream_t s, int which) {
     return 0;
 }
 
+// narrow rows (one float4 per lane, the aggregate-then-project layer): a whole short segment in flight at once
+static int split_variant_narrow() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_SPLIT_VARIANT1"); v = e ? atoi(e) : 0; if (v < 0 || v > 4) v = 0; }
+    return v;
+}
+
 template <int NCH, int HT>
 int launch_split_pass(const BwdSplitArgs& a, cudaStream_t s, int which) {
-    if constexpr (NCH <= 2) {
+    if constexpr (NCH == 1) {
+        switch (split_variant_narrow()) {
+            // measured at C2 (cols / rels ms): <4,4> 3.79 / 1.94, <8,3> 4.34 / 2.09, <8,4> 4.27 / 2.01, <16,3> 5.54 / 2.66,
+            // <16,2> 6.41 / 2.63: fewer warps lose more than deeper gathers win (short columns: latency chains, not bytes)
+            case 1: return launch_split_passes<NCH, HT, 2, 6>(a, s, which);
+            case 2: return launch_split_passes<NCH, HT, 2, 8>(a, s, which);
+            case 3: return launch_split_passes<NCH, HT, 4, 5>(a, s, which);
+            case 4: return launch_split_passes<NCH, HT, 4, 6>(a, s, which);
+            default: return launch_split_passes<NCH, HT, 4, 4>(a, s, which);
+        }
+    } else if constexpr (NCH <= 2) {
         switch (split_variant()) {
             case 1: return launch_split_passes<NCH, HT, 4, 3>(a, s, which);
             case 2: return launch_split_passes<NCH, HT, 2, 4>(a, s, which);

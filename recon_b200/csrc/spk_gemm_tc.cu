@@ -258,7 +258,11 @@ gemm_nn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
             mbar_wait(tfull(acc), aph);
             tc_fence_after();
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            // A warp whose 32 rows lie past the last row of C has nothing to store, and it must not touch its staging buffers:
+            // it commits no bulk group, so `wait_group.read 1` would keep admitting the LAST store of the previous tile as
+            // the one allowed reader while its buffer is rewritten with this tile's zeros (lost C += rows; found by
+            // test_gemm_nn[20000-52-416]: M tiles 156 = 2 x 148 CTAs + partial last tile).
+            for (int c0 = 0; c0 < p.BN && row0 < p.M; c0 += 32) {
                 if (n0 + c0 >= p.N) break;
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
@@ -531,7 +535,11 @@ gemm_nn_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int n0 = (int)(tile % p.n_tiles_n) * p.BN;
             mbar_wait_cluster(tfull(acc), aph);
             tc_fence_after();
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            // A warp whose 32 rows lie past the last row of C has nothing to store, and it must not touch its staging buffers:
+            // it commits no bulk group, so `wait_group.read 1` would keep admitting the LAST store of the previous tile as
+            // the one allowed reader while its buffer is rewritten with this tile's zeros (lost C += rows; found by
+            // test_gemm_nn[20000-52-416]: M tiles 156 = 2 x 148 CTAs + partial last tile).
+            for (int c0 = 0; c0 < p.BN && row0 < p.M; c0 += 32) {
                 if (n0 + c0 >= p.N) break;
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + acc * 256u + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);

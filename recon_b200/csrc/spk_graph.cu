@@ -109,6 +109,65 @@ rs_scan_kernel(unsigned* __restrict__ data, long len) {
     }
 }
 
+// Multi-CTA form of the same scan (the single-CTA loop over 256 * nblk counters took 0.39 ms per radix pass at 20M keys,
+// half of the whole CSR / CSC / relation build): per-tile totals, the single-CTA scan of those few hundred totals, then
+// every tile rescans itself on top of its base.
+constexpr int SCN_TILE = 4096;                     // 1024 threads x 4 counters
+
+__device__ __forceinline__ unsigned scn_tile_excl(unsigned tsum, unsigned* warp_tot, unsigned& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const unsigned w = warp_tot[lane];
+        unsigned winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_tot[lane] = winc - w;
+        if (lane == 31) warp_tot[32] = winc;
+    }
+    __syncthreads();
+    total = warp_tot[32];
+    return warp_tot[wid] + (inc - tsum);
+}
+
+__global__ void __launch_bounds__(1024)
+rs_scan_tile_sums_kernel(const unsigned* __restrict__ data, long len, unsigned* __restrict__ sums) {
+    __shared__ unsigned warp_tot[33];
+    const long i0 = (long)blockIdx.x * SCN_TILE + (long)threadIdx.x * 4;
+    unsigned tsum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tsum += (i0 + k < len) ? data[i0 + k] : 0u;
+    unsigned total;
+    scn_tile_excl(tsum, warp_tot, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+rs_scan_apply_kernel(unsigned* __restrict__ data, long len, const unsigned* __restrict__ sums) {
+    __shared__ unsigned warp_tot[33];
+    const long i0 = (long)blockIdx.x * SCN_TILE + (long)threadIdx.x * 4;
+    unsigned v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < len) ? data[i0 + k] : 0u;
+    unsigned total;
+    unsigned excl = scn_tile_excl(v[0] + v[1] + v[2] + v[3], warp_tot, total) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k < len) data[i0 + k] = excl;
+        excl += v[k];
+    }
+}
+
 // Stable scatter: warp w of a CTA owns keys [tile + w*RS_WARP_SPAN, +RS_WARP_SPAN) and walks them in order.
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter_kernel(const int* __restrict__ keys, const int* __restrict__ vals, long n, int shift,
@@ -197,7 +256,7 @@ int iota_i32(int* v, long n, cudaStream_t s) {
 
 long radix_sort_workspace_bytes(long n) {
     const long nblk = (n + RS_TILE - 1) / RS_TILE;
-    return (256L * nblk + 16) * sizeof(unsigned);
+    return (256L * nblk + 16 + (256L * nblk + SCN_TILE - 1) / SCN_TILE + 16) * sizeof(unsigned);   // histogram + tile sums of its scan
 }
 
 // Sorts (keys, vals) by the low `key_bits` bits of the key; stable. Uses (keys_tmp, vals_tmp) as ping-pong
@@ -214,8 +273,20 @@ int radix_sort_pairs(int* keys, int* vals, int* keys_tmp, int* vals_tmp, long n,
         const int shift = 8 * p;
         rs_hist_kernel<<<nblk, RS_THREADS, 0, s>>>(kin, n, shift, hist, nblk);
         if (int rc = check_launch("rs_hist")) return rc;
-        rs_scan_kernel<<<1, 1024, 0, s>>>(hist, 256L * nblk);
-        if (int rc = check_launch("rs_scan")) return rc;
+        const long len = 256L * nblk;
+        const long ntiles = (len + SCN_TILE - 1) / SCN_TILE;
+        if (ntiles <= 2) {
+            rs_scan_kernel<<<1, 1024, 0, s>>>(hist, len);
+            if (int rc = check_launch("rs_scan")) return rc;
+        } else {
+            unsigned* sums = hist + len + 16;
+            rs_scan_tile_sums_kernel<<<(unsigned)ntiles, 1024, 0, s>>>(hist, len, sums);
+            if (int rc = check_launch("rs_scan_tile_sums")) return rc;
+            rs_scan_kernel<<<1, 1024, 0, s>>>(sums, ntiles);
+            if (int rc = check_launch("rs_scan")) return rc;
+            rs_scan_apply_kernel<<<(unsigned)ntiles, 1024, 0, s>>>(hist, len, sums);
+            if (int rc = check_launch("rs_scan_apply")) return rc;
+        }
         rs_scatter_kernel<<<nblk, RS_THREADS, 0, s>>>(kin, vin, n, shift, hist, nblk, kout, vout);
         if (int rc = check_launch("rs_scatter")) return rc;
         int* t = kin; kin = kout; kout = t;

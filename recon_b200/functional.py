@@ -131,12 +131,30 @@ def tc_friendly(X):
     return Xp[:, :f]
 
 
+# The aggregate-then-project layer builds a table whose rows START with the input row x at a 16-byte aligned stride
+# (X~ = [x | pad | score scalars]); a later X @ W on the same tensor (entity_embeddings.mm(W_entities), models.py:175) reads
+# its operand from that table instead of making a padded copy of the [N, 50] matrix for TMA (0.33 ms per step at C2).
+_X_TABLE = {"key": None, "table": None}
+
+
+def _x_key(X):
+    return (X.data_ptr(), X._version, tuple(X.shape), tuple(X.stride()), str(X.device))
+
+
+def _tma_operand(X):
+    if _X_TABLE["key"] is not None and _X_TABLE["key"] == _x_key(X) and USE_TC:
+        t = _X_TABLE["table"]
+        _X_TABLE["key"] = _X_TABLE["table"] = None          # one-shot: the table is only trusted right after it was built
+        return t[:, :X.shape[1]]
+    return tc_friendly(X.contiguous())
+
+
 class MatMulFn(torch.autograd.Function):
     """X @ W with the library GEMMs (relation_embed.mm(W) models.py:77, entity_embeddings.mm(W_entities) 175)."""
 
     @staticmethod
     def forward(ctx, X, W, dist=None):
-        X = tc_friendly(X.contiguous()); W = W.contiguous()
+        X = _tma_operand(X); W = W.contiguous()
         ctx.save_for_backward(X, W)
         ctx.dist = dist
         return gemm_nn(X, W)
@@ -607,6 +625,7 @@ class AggGroupFn(torch.autograd.Function):
             Xt = _agg_table(X, V, geom.LX, geom.Fx4)
             Xc = Xt
             Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
+            _X_TABLE["key"], _X_TABLE["table"] = _x_key(X), Xt
         else:
             Xc, Xt = dist.gather_buffer(geom.LX, dev)
             _agg_table(X, V, geom.LX, geom.Fx4, out=Xt)

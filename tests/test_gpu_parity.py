@@ -131,6 +131,20 @@ def test_gemm_nn(m, k, n, gemm_path):
     assert rel_l2(c2, c0.double() + a.double() @ b.double()) < tol
 
 
+def test_gemm_nn_partial_last_tile_keeps_every_update():
+    """157 M tiles on 148 persistent CTAs with a partial last tile: the epilogue warps whose rows lie past M used to rewrite
+    their staging buffers while the previous tile's last TMA reduce-add was still reading them (lost C += rows, 30 % of runs)."""
+    from recon_b200.functional import gemm_nn
+    m, k, n = 20000, 52, 416
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(m, k, generator=g); b = torch.randn(k, n, generator=g); c0 = torch.randn(m, n, generator=g)
+    ad, bd, c0d = a.to(dev()), b.to(dev()), c0.to(dev())
+    ref = c0.double() + a.double() @ b.double()
+    for _ in range(12):
+        c = gemm_nn(ad, bd, out=c0d.clone(), accumulate=True)
+        assert rel_l2(c, ref) < 1e-5
+
+
 def test_gemm_nn_tc_wide_dynamic_range():
     """3xTF32 must stay fp32-accurate when magnitudes vary over many binades."""
     from recon_b200.functional import gemm_nn
