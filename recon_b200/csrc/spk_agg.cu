@@ -395,11 +395,10 @@ agg_fwd_stream_kernel(const AggFwdArgs a) {
 // with four R2UR each (UBLKCP takes uniform registers) plus the mbarrier bookkeeping. A gathered row here is ONE float4
 // per lane (X~[j] chunk in lanes 0-15, Rel~[k] chunk in lanes 16-31), so a plain LDG.128 per lane per edge with AG_U edges
 // in flight costs AG_U registers per lane, not the 16+ the 832-byte rows of K2 needed: the latency depth fits registers.
-constexpr int AG_U = 8;
 constexpr int AGR_WARPS = 8;
 
-template <int HT, bool HAS2, bool TASKS>
-__global__ void __launch_bounds__(AGR_WARPS * 32, 2)
+template <int HT, bool HAS2, bool TASKS, int AG_U, int MINB>
+__global__ void __launch_bounds__(AGR_WARPS * 32, MINB)
 agg_fwd_reg_kernel(const AggFwdArgs a) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int H = a.g.H;
@@ -570,17 +569,29 @@ static bool agg_fwd_ring() {
     return e && e[0] == 'r';
 }
 
+static int agg_fwd_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_AGG_FWD_VARIANT"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; }
+    return v;
+}
+
 template <int HT, bool HAS2>
 int launch_agg_fwd_t(const AggFwdArgs& a, cudaStream_t s) {
     if (!agg_fwd_ring()) {
         if (a.n_rows > 0) {
             const unsigned grid = (unsigned)((a.n_rows + 32L * AGR_WARPS - 1) / (32L * AGR_WARPS));
-            agg_fwd_reg_kernel<HT, HAS2, false><<<grid, AGR_WARPS * 32, 0, s>>>(a);
+            // (gathers in flight per warp, CTAs of 8 warps per SM), measured at C2: <4,3> 2.82 ms, <8,2> 3.01, <4,4> 3.16,
+            // <8,3> 3.36, <16,2> 3.63 -- neither more warps nor deeper gathers is the limiter here
+            switch (agg_fwd_variant()) {
+                case 1: agg_fwd_reg_kernel<HT, HAS2, false, 8, 2><<<grid, AGR_WARPS * 32, 0, s>>>(a); break;
+                case 2: agg_fwd_reg_kernel<HT, HAS2, false, 4, 4><<<grid, AGR_WARPS * 32, 0, s>>>(a); break;
+                default: agg_fwd_reg_kernel<HT, HAS2, false, 4, 3><<<grid, AGR_WARPS * 32, 0, s>>>(a); break;
+            }
             if (int rc = check_launch("agg_fwd_reg_rows")) return rc;
         }
         if (a.hub.n_tasks > 0) {
             const unsigned grid = (a.hub.n_tasks + AGR_WARPS - 1) / AGR_WARPS;
-            agg_fwd_reg_kernel<HT, HAS2, true><<<grid, AGR_WARPS * 32, 0, s>>>(a);
+            agg_fwd_reg_kernel<HT, HAS2, true, 8, 2><<<grid, AGR_WARPS * 32, 0, s>>>(a);
             if (int rc = check_launch("agg_fwd_reg_tasks")) return rc;
             agg_fwd_hub_finalize_kernel<HT><<<a.hub.n_hubs, 1024, 0, s>>>(a);
             if (int rc = check_launch("agg_fwd_hub_finalize")) return rc;

@@ -177,19 +177,28 @@ __device__ __forceinline__ void split_cols_accumulate(const BwdSplitArgs& a, int
 template <int NCH, int HT, int U, int MINB>
 __global__ void __launch_bounds__(SPK_CTA_THREADS, MINB)
 split_cols_kernel(const BwdSplitArgs a) {
+    // persistent warps (grid = resident CTAs): warp w walks columns w, w + W, w + 2W, ... with the pointers of its next column
+    // requested one column ahead, so neighbouring warps still work on neighbouring columns and a warp's dependent chain
+    // (pointers -> indices -> row gathers) overlaps across its columns; no CTA turnover for 10-edge columns
     const int lane = threadIdx.x & 31;
-    const int colj = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
+    const int nw = gridDim.x * SPK_WARPS_PER_CTA;
+    int colj = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (colj >= a.n_cols) return;
-    const int beg = __ldg(a.colptr + colj), end = __ldg(a.colptr + colj + 1);
-    if (end - beg > a.col_hub.hub_thresh) return;
-    SplitAcc<NCH, HT> st;
-    split_acc_init<NCH, HT>(st);
-    if (end > beg) {
-        SegCtx<NCH, HT> cc;
-        seg_ctx_load<NCH, HT>(a.P2 + (long)colj * a.ld2, a.g, lane, cc, a.dup);
-        split_cols_accumulate<NCH, HT, U>(a, beg, end, lane, cc, st);
+    // (also prefetching the next column's first index batch cost more in spills than it hid: cols 4.2 -> 4.8 ms)
+    int beg_n = __ldg(a.colptr + colj), end_n = __ldg(a.colptr + colj + 1);
+    for (; colj < a.n_cols; colj += nw) {
+        const int beg = beg_n, end = end_n;
+        if (colj + nw < a.n_cols) { beg_n = __ldg(a.colptr + colj + nw); end_n = __ldg(a.colptr + colj + nw + 1); }
+        if (end - beg > a.col_hub.hub_thresh) continue;
+        SplitAcc<NCH, HT> st;
+        split_acc_init<NCH, HT>(st);
+        if (end > beg) {
+            SegCtx<NCH, HT> cc;
+            seg_ctx_load<NCH, HT>(a.P2 + (long)colj * a.ld2, a.g, lane, cc, a.dup);
+            split_cols_accumulate<NCH, HT, U>(a, beg, end, lane, cc, st);
+        }
+        split_store<NCH, HT>(a.dP2 + (long)colj * a.ldd2, a.g, lane, st);
     }
-    split_store<NCH, HT>(a.dP2 + (long)colj * a.ldd2, a.g, lane, st);
 }
 
 template <int NCH, int HT, int U, int MINB>
@@ -274,6 +283,8 @@ split_rels_kernel(const BwdSplitArgs a) {
 template <int NCH, int HT, int U, int MINB>
 __global__ void __launch_bounds__(SPK_CTA_THREADS, MINB)
 split_rels_tasks_kernel(const BwdSplitArgs a) {
+    // (one warp per task: persistent warps walking slots w, w + W, ... were measured 2-20 % slower here -- they stretch the row
+    //  window that the launch order keeps L2-resident)
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * SPK_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (slot >= a.rel_hub.n_tasks) return;
@@ -401,11 +412,27 @@ static int split_variant() {
     return v;
 }
 
+static int sm_count() {
+    static int n[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (n[dev] == 0) { int v = 148; cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); n[dev] = v > 0 ? v : 148; }
+    return n[dev];
+}
+// SPK_SPLIT_PERSIST = waves of resident CTAs in the column-pass grid (0: one warp per column, the round-1 launch)
+static int split_persist() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SPK_SPLIT_PERSIST"); v = e ? atoi(e) : 8; if (v < 0 || v > 64) v = 8; }
+    return v;
+}
+
 template <int NCH, int HT, int U, int MINB>
 int launch_split_passes(const BwdSplitArgs& a, cudaStream_t s, int which) {
     if (which == 0) {
         if (a.n_cols > 0) {
-            const unsigned grid = (a.n_cols + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+            const unsigned full = (a.n_cols + SPK_WARPS_PER_CTA - 1) / SPK_WARPS_PER_CTA;
+            const unsigned resident = (unsigned)(sm_count() * MINB) * (unsigned)split_persist();
+            const unsigned grid = (split_persist() > 0 && full > resident) ? resident : full;
             split_cols_kernel<NCH, HT, U, MINB><<<grid, SPK_CTA_THREADS, 0, s>>>(a);
             if (int rc = check_launch("split_cols")) return rc;
         }

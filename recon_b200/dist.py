@@ -304,6 +304,7 @@ class PartitionedKBGAT:
             gen = torch.Generator().manual_seed(1)
             self.g_ent = torch.randn(out_e.shape, generator=gen).to(self.device)
             self.g_rel = torch.randn(out_r.shape, generator=gen).to(self.device)
+        from . import functional as SF
         loss = SF.linear_loss_backward((out_e, out_r), (self.g_ent, self.g_rel))
         return out_e, out_r, loss
 
