@@ -116,7 +116,8 @@ typedef struct {
     float* out; int64_t ldo;                     /* [n_rows, H*D] */
     float* den; float* sw;                       /* [n_rows, H] */
     int32_t* nanflag;                            /* sticky: set to 1 where the reference would assert (layers.py:147,167,172) */
-    int32_t n_rows; int32_t apply_elu; float alpha; int32_t reserved;
+    int32_t n_rows; int32_t apply_elu; float alpha;
+    int32_t elu_rows;                            /* > 0 with apply_elu: ELU only on rows < elu_rows (0: all rows) */
     spk_geom geom;
     spk_hub_tasks hub;
 } spk_edge_fwd_args;

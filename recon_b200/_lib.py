@@ -37,7 +37,7 @@ class EdgeFwdArgs(C.Structure):
                 ("mask", C.c_void_p), ("mask_stride", C.c_int64),
                 ("out", C.c_void_p), ("ldo", C.c_int64), ("den", C.c_void_p), ("sw", C.c_void_p),
                 ("nanflag", C.c_void_p),
-                ("n_rows", C.c_int32), ("apply_elu", C.c_int32), ("alpha", C.c_float), ("reserved", C.c_int32),
+                ("n_rows", C.c_int32), ("apply_elu", C.c_int32), ("alpha", C.c_float), ("elu_rows", C.c_int32),
                 ("geom", Geom), ("hub", HubTasks)]
 
 

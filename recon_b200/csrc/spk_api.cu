@@ -183,6 +183,7 @@ int spk_edge_attn_fwd(const spk_edge_fwd_args* p, spk_stream_t stream) {
     a.mask = p->mask; a.mask_stride = p->mask_stride;
     a.out = p->out; a.ldo = p->ldo; a.den = p->den; a.sw = p->sw; a.nanflag = p->nanflag;
     a.n_rows = p->n_rows; a.alpha = p->alpha; a.apply_elu = p->apply_elu;
+    a.elu_rows = p->elu_rows > 0 ? p->elu_rows : 0x7fffffff;
     a.out_vec = (p->geom.d_head % 4 == 0) && (p->ldo % 4 == 0) && aligned16(p->out);
     a.hub = hub_of(p->hub);
     if (a.hub.n_tasks > 0 && (a.hub.ldpart < p->geom.width + 2 * SPK_MAX_HEADS || (a.hub.ldpart & 3) || !aligned16(a.hub.partial))) {

@@ -42,6 +42,8 @@ struct EdgeFwdArgs {
     LayerGeom g;
     float alpha;
     int apply_elu;
+    int elu_rows;             // with apply_elu: only rows < elu_rows get the ELU (rows behind them are partial sums that a
+                              // caller combines first: the ghost rows of hub rows split across ranks)
     int out_vec;              // out rows may be stored as float4
     HubTasks hub;
 };

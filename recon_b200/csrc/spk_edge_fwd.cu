@@ -149,7 +149,7 @@ __device__ __forceinline__ void fwd_finalize(const EdgeFwdArgs& a, int row, int 
         for (int k = 0; k < 4; ++k) {
             o[k] = o[k] * d;                                  // layers.py:169 (NaN in num or 0*inf both surface here: 167, 172)
             bad |= (o[k] != o[k]);
-            if (a.apply_elu) o[k] = elu1(o[k]);
+            if (a.apply_elu && row < a.elu_rows) o[k] = elu1(o[k]);
         }
         const int off = (c4 - h * g.Dp4) * 4;
         float* dst = a.out + (long)row * a.ldo + (long)h * g.D + off;

@@ -20,6 +20,55 @@
 #include <atomic>
 #include <thread>
 #include <vector>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+
+namespace {
+// Minimal persistent worker pool for the host-side packers (one job at a time; callers are serialised by the mutex).
+class PackPool {
+public:
+    ~PackPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; ++gen_; }
+        go_.notify_all();
+        for (auto& t : th_) if (t.joinable()) t.join();
+    }
+    void run(int n, const std::function<void(int)>& f) {
+        std::lock_guard<std::mutex> serial(run_m_);
+        std::unique_lock<std::mutex> lk(m_);
+        while ((int)th_.size() < n) { const int id = (int)th_.size(); th_.emplace_back([this, id] { loop(id); }); }
+        job_ = &f; active_ = n; pending_ = n; ++gen_;
+        go_.notify_all();
+        done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            go_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            if (stop_) return;
+            if (id >= active_) continue;
+            const std::function<void(int)>* f = job_;
+            lk.unlock();
+            (*f)(id);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_, run_m_;
+    std::condition_variable go_, done_;
+    const std::function<void(int)>* job_ = nullptr;
+    uint64_t gen_ = 0;
+    int active_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
+PackPool& pack_pool() { static PackPool* p = new PackPool(); return *p; }   // leaked on purpose: no join at process exit
+}  // namespace
+
 
 namespace spk {
 void set_error(const char* fmt, ...);
@@ -351,13 +400,13 @@ int spk_pack_index_host(const int64_t* src, int64_t n, int64_t stride, int64_t l
     };
     if (nt == 1) work(0, n);
     else {
-        std::vector<std::thread> th;
+        // persistent workers: the stager calls this once per 16 MB chunk, and spawning up to 64 threads per call cost more
+        // than packing the chunk
         const int64_t chunk = (n + nt - 1) / nt;
-        for (int t = 0; t < nt; ++t) {
+        pack_pool().run(nt, [&](int t) {
             const int64_t b = std::min(n, (int64_t)t * chunk), e = std::min(n, b + chunk);
-            if (b < e) th.emplace_back(work, b, e);
-        }
-        for (auto& x : th) x.join();
+            if (b < e) work(b, e);
+        });
     }
     if (bad.load()) { spk::set_error("pack_index_host: index outside [%lld, %lld)", (long long)lo, (long long)hi); return 5; }
     return 0;

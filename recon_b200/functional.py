@@ -183,8 +183,9 @@ def _hub_partial(hubs, ldpart, device):
     return torch.empty(hubs.n_tasks, ldpart, dtype=torch.float32, device=device)
 
 
-def edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag):
-    """K2 launch. P1/P2: [n, >=Wd] views with unit inner stride; returns (out [N,H*D], den [N,H], sw [N,H])."""
+def edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanflag, elu_rows=0):
+    """K2 launch. P1/P2: [n, >=Wd] views with unit inner stride; returns (out [N,H*D], den [N,H], sw [N,H]).
+    elu_rows > 0: the ELU is applied to rows < elu_rows only."""
     lib = _lib.load()
     n = graph.n_nodes
     dev = P1.device
@@ -201,7 +202,7 @@ def edge_attn_forward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, nanfl
         a.mask = mask_csr.data_ptr(); a.mask_stride = mask_csr.stride(0)
     a.out = out.data_ptr(); a.ldo = out.stride(0); a.den = den.data_ptr(); a.sw = sw.data_ptr()
     a.nanflag = nanflag.data_ptr()
-    a.n_rows = n; a.apply_elu = int(apply_elu); a.alpha = float(alpha)
+    a.n_rows = n; a.apply_elu = int(apply_elu); a.alpha = float(alpha); a.elu_rows = int(elu_rows)
     a.geom = geom.struct()
     ldpart = geom.Wd + 2 * MAX_HEADS
     partial = _hub_partial(graph.row_hubs, ldpart, dev)
@@ -425,11 +426,15 @@ class AttentionGroupFn(torch.autograd.Function):
             out_ret = out
         else:
             n = X.shape[0]
-            out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, False, mask_csr, nanflag)
+            # the kernel applies the ELU to this rank's own rows; the ghost rows behind them come out as num_loc / den_loc and
+            # get theirs after the partial sums of all ranks are combined (a few rows, not a pass over the whole output)
+            k_elu = bool(apply_elu) and n > 0                    # (a rank may own no rows at all: then every row is a ghost row)
+            out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, k_elu, mask_csr, nanflag, elu_rows=n if k_elu else 0)
             _ghost_combine(ghost, out, den, sw, n, geom.H)
             nanflag.add_(torch.isnan(out[n:]).any().to(torch.int32))
-            if apply_elu:
-                _lib.check(_lib.load().spk_elu_inplace(_lib.ptr(out), out.stride(0), out.shape[0], out.shape[1],
+            if apply_elu and out.shape[0] > n:
+                tail = out[n:]
+                _lib.check(_lib.load().spk_elu_inplace(_lib.ptr(tail), tail.stride(0), tail.shape[0], tail.shape[1],
                                                        _lib.stream_ptr()), "elu_inplace")
             out[ghost.mine_local] = out[n:][ghost.mine]          # the owner's copy of a hub row takes the combined result
             out_ret = out[:n]

@@ -132,6 +132,7 @@ def _segment_ptr(sorted_keys, n_seg):
     return ptr
 
 
+PACK_CHUNK = int(os.environ.get("SPK_PACK_CHUNK", str(4 << 20)))      # elements per pack + copy step of the host stager
 _STAGING = {}          # device index -> {"buf": pinned int32 tensor, "event": last H2D that read it, "stream": copy stream}
 
 
@@ -182,19 +183,26 @@ class _HostStager:
         k = self.ORDER.index(name)
         src, hop_col, hi = self.plan[name]
         seg = self.buf[k * self.e:(k + 1) * self.e]
-        rc = 0
-        if src is not None:
-            rc = lib.spk_pack_index_host(src if self.e1 else None, self.e1, 1, 0, hi, seg.data_ptr(), 0)
-        elif self.e1:
-            seg[:self.e1].fill_(-1)                        # t2 of a 1-hop edge
-        if rc == 0 and self.has2:
-            rc = lib.spk_pack_index_host(self.nhop.data_ptr() + 8 * hop_col, self.e2, 4, 0, hi, seg.data_ptr() + 4 * self.e1, 0)
-        if rc == 5:
-            raise IndexError("edge / relation index out of range for the given entity / relation tables")
-        _lib.check(rc, "pack_index_host")
         dev_arr = self.dev.pop(name)
+        # packed and copied in chunks: the link starts after the first 16 MB instead of after the whole array, so packing and
+        # transfer of one array overlap as well (not only the transfer of one array with the packing of the next)
+        spans = [(0, self.e1, src, 1)] if self.e1 else []
+        if self.has2:
+            spans.append((self.e1, self.e, self.nhop.data_ptr() + 8 * hop_col, 4))
+        for s0, s1, sp, stride in spans:
+            for c0 in range(s0, s1, PACK_CHUNK):
+                c1 = min(s1, c0 + PACK_CHUNK)
+                if sp is None:
+                    seg[c0:c1].fill_(-1)                   # t2 of a 1-hop edge
+                    rc = 0
+                else:
+                    rc = lib.spk_pack_index_host(sp + 8 * stride * (c0 - s0), c1 - c0, stride, 0, hi, seg.data_ptr() + 4 * c0, 0)
+                if rc == 5:
+                    raise IndexError("edge / relation index out of range for the given entity / relation tables")
+                _lib.check(rc, "pack_index_host")
+                with torch.cuda.stream(self.cs):
+                    dev_arr[c0:c1].copy_(seg[c0:c1], non_blocking=True)
         with torch.cuda.stream(self.cs):
-            dev_arr.copy_(seg, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self.cs)
         self.st["event"] = ev
