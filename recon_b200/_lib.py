@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspkbgat.so")
+LIB_PATH = os.environ.get("SPK_LIB") or os.path.join(_HERE, "libspkbgat.so")     # SPK_LIB: A/B builds of the same ABI
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)

@@ -74,6 +74,8 @@ __device__ __forceinline__ void split_store(float* dst, const LayerGeom& g, int 
     }
 }
 
+// (row gathers stay on ld.global.nc with L1 allocation: with L2-only loads (ld.global.cg / L1::no_allocate) the column pass
+//  gained 2 % but the windowed relation pass went 2.25 -> 3.9-4.2 ms -- the G rows of its window are also reused out of L1)
 // gathers of the U edges starting at batch position u0 (rows broadcast from the lanes that hold them)
 template <int NCH, int U>
 __device__ __forceinline__ void gather_rows(const float* __restrict__ G, long ldg, int Dt4, int my_row, int u0, int n, int lane,
