@@ -11,8 +11,8 @@ import sys
 
 GROUPS = {                                  # bench.py roofline key -> kernels the call launches (C2: layer 2 = <NCH 2, H 1>)
     "c2:edge_attn_fwd": r"edge_fwd_stream_kernel|edge_fwd_hub_finalize",
-    "c2:edge_attn_bwd_split:cols": r"split_cols",
-    "c2:edge_attn_bwd_split:rels": r"split_rels",
+    "c2:edge_attn_bwd_split:cols": r"split_cols_(tasks_)?kernel<2, 1",       # (layer 1 runs the <1, 2, ..> instances)
+    "c2:edge_attn_bwd_split:rels": r"split_rels_(tasks_)?kernel<2, 1",
     "c2:edge_attn_bwd_split:node": r"bwd_node_kernel",
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
