@@ -23,6 +23,9 @@ USE_TC = True          # route eligible products through the tcgen05 3xTF32 GEMM
 TC_MIN_ROWS = 1        # (tests lower/raise this to exercise both paths)
 
 
+WD_ALIGN = int(os.environ.get("SPK_WD_ALIGN", "8"))     # projected-row width granularity in floats (8 = one 32-byte sector)
+
+
 class Geometry:
     """Row format of the projected tables for H heads of width D (see include/spkbgat.h)."""
 
@@ -31,7 +34,9 @@ class Geometry:
         self.H, self.D = n_heads, d_head
         self.Dp = (d_head + 3) // 4 * 4
         self.Dt = self.H * self.Dp
-        self.Wd = (self.Dt + self.H + 7) // 8 * 8
+        self.Wd = (self.Dt + self.H + WD_ALIGN - 1) // WD_ALIGN * WD_ALIGN
+        if self.Wd > 512 and WD_ALIGN > 8:
+            self.Wd = (self.Dt + self.H + 7) // 8 * 8
         if self.Wd > 512:
             raise ValueError(f"heads*out_features = {n_heads}*{d_head} exceeds the 512-float fused row")
 
@@ -250,7 +255,7 @@ def edge_attn_backward(graph, P1, P2, P3, geom, alpha, apply_elu, mask_csr, out,
     lib = _lib.load()
     graph.build_backward()
     n, dev = graph.n_nodes, P1.device
-    ldg = (geom.Dt + 7) // 8 * 8
+    ldg = _row_stride(geom.Dt, G_ALIGN)
     G = torch.empty(n, ldg, dtype=torch.float32, device=dev)
     mode = BWD_MODE if sw is not None else "rows"
     if mode == "split" and graph.t2 is not None:
@@ -547,6 +552,18 @@ AGG_BWD_MODE = os.environ.get("SPK_AGG_BWD_MODE", "split")     # "split": split-
 AGG_MAX_HEADS = 2
 
 
+# Row strides (floats) of the tables that are gathered one row per edge; the default keeps whole 32-byte sectors (8 floats),
+# SPK_*_ALIGN = 16 / 32 rounds rows to 64 / 128 bytes so that a row never straddles one DRAM burst / cache line more than its
+# size needs (more bytes per row, fewer partially used lines).
+G_ALIGN = int(os.environ.get("SPK_G_ALIGN", "8"))
+GX_ALIGN = int(os.environ.get("SPK_GX_ALIGN", "8"))
+LX_ALIGN = int(os.environ.get("SPK_LX_ALIGN", "8"))
+
+
+def _row_stride(width, align):
+    return (width + align - 1) // align * align
+
+
 class AggGeometry:
     """Shapes of the aggregate-then-project path (csrc/spk_agg.cuh): table rows [x | pad | 4 scalars | pad]."""
 
@@ -554,8 +571,8 @@ class AggGeometry:
         self.H, self.F, self.Rd, self.D = n_heads, in_features, nrela_dim, d_head
         self.Fx4, self.Fr4 = (in_features + 3) // 4, (nrela_dim + 3) // 4
         self.Fp, self.Rp = 4 * self.Fx4, 4 * self.Fr4
-        self.LX = (self.Fp + 4 + 7) // 8 * 8
-        self.LR = (self.Rp + 4 + 7) // 8 * 8
+        self.LX = _row_stride(self.Fp + 4, LX_ALIGN)
+        self.LR = _row_stride(self.Rp + 4, LX_ALIGN)
         self.LZ = 2 * self.Fp + self.Rp
 
     @staticmethod
@@ -702,8 +719,8 @@ class AggGroupFn(torch.autograd.Function):
                 gemm_tn(Z[:n_loc, h * LZ:(h + 1) * LZ], dh[:n_loc], out=dWa[h])
                 gemm_tn((Z[n_loc:, h * LZ:(h + 1) * LZ] * ghost.mine.unsqueeze(1)).contiguous(), dh[n_loc:], out=dWa[h],
                         accumulate=True)
-        Gx = torch.empty(n, H * Fp, **f32)
-        Gr = torch.empty(n, H * Rp, **f32)
+        Gx = torch.empty(n, _row_stride(H * Fp, GX_ALIGN), **f32)[:, :H * Fp]     # rows gathered per edge: stride rounded so
+        Gr = torch.empty(n, _row_stride(H * Rp, GX_ALIGN), **f32)[:, :H * Rp]     # that a row does not straddle extra lines
         rowout = torch.empty(n, Fp + 4, **f32)
         a = _lib.AggBwdArgs()
         a.xrow = Xt.data_ptr(); a.ldxr = Xt.stride(0)
