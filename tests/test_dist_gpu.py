@@ -21,10 +21,15 @@ def _free_port():
 def test_partitioned_matches_single_gpu(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(ROOT, "tests", "dist_gpu_check.py")]
-    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    for attempt in range(2):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+               os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+        p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+        # a launch that never reached the first comparison (rendezvous / port / NCCL start-up trouble right after the
+        # previous world's job, seen once on an 8-GPU box) is retried once; a parity result is never retried
+        if p.returncode == 0 or "DIST PARITY" in p.stdout:
+            break
     assert p.returncode == 0 and "DIST PARITY OK" in p.stdout, (p.stdout[-3000:], p.stderr[-3000:])
 
 
