@@ -284,6 +284,27 @@ int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t 
 /* out[0] (+)= <a, b> over n contiguous floats (16-byte aligned), deterministic (fixed chunking, fp64 across threads):
  * the linear probe loss <out_entity, G_e> + <out_relation, G_r> of SURVEY.md 8d (the reference's step writes it as
  * (out * G).sum()). workspace: spk_inner_product_workspace_bytes() bytes of device memory. */
+/* ---- extended weight matrices from the reference-shaped attention parameters a_h [D, 2F+Rd], a_2,h [1, D]
+ *      (GAT/layers.py:100-105), and the gradients back to them: replaces the slice assignments / a.t() / (a^T * a_2).sum()
+ *      glue and its autograd.
+ *   mode 0 (projected tables, spk_geom):   W0 = Wn [F, ld0 >= 2*width], W1 = Wr [Rd, ld1 >= width]
+ *   mode 1 (aggregate-then-project):       W0 = Wa [n_heads, lz, D] (dense), W1 = V [F, 4], W2 = V3 [Rd, 4]
+ * spk_attn_weights_fwd zero-fills the outputs and scatters a^T and a^T a_2^T; spk_attn_weights_bwd reads the gradients of
+ * the same buffers from W0 / W1 / W2 and writes da[h] (like a[h]) and da2[h] ([D]). n_heads <= 4. ---- */
+typedef struct {
+    const float* a[4]; const float* a2[4];
+    float* da[4]; float* da2[4];
+    int32_t n_heads, F, Rd, D;
+    int32_t mode; int32_t d_pad, width;         /* mode 0: spk_geom.d_pad / width */
+    int32_t f_pad, lz;                           /* mode 1: F rounded up to 4; rows per head of Wa (2 * f_pad + Rd rounded up to 4) */
+    int32_t reserved;
+    float* W0; int64_t ld0;
+    float* W1; int64_t ld1;
+    float* W2;
+} spk_attn_weights_args;
+int spk_attn_weights_fwd(const spk_attn_weights_args* args, spk_stream_t stream);
+int spk_attn_weights_bwd(const spk_attn_weights_args* args, spk_stream_t stream);
+
 int64_t spk_inner_product_workspace_bytes(void);
 int spk_inner_product(const float* a, const float* b, int64_t n, void* workspace, float* out, int32_t accumulate,
                       spk_stream_t stream);

@@ -147,6 +147,14 @@ class SgdArgs(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/spkbgat.h declares
+class AttnWeightsArgs(C.Structure):
+    _fields_ = [("a", C.c_void_p * 4), ("a2", C.c_void_p * 4), ("da", C.c_void_p * 4), ("da2", C.c_void_p * 4),
+                ("n_heads", C.c_int32), ("F", C.c_int32), ("Rd", C.c_int32), ("D", C.c_int32),
+                ("mode", C.c_int32), ("d_pad", C.c_int32), ("width", C.c_int32),
+                ("f_pad", C.c_int32), ("lz", C.c_int32), ("reserved", C.c_int32),
+                ("W0", C.c_void_p), ("ld0", C.c_int64), ("W1", C.c_void_p), ("ld1", C.c_int64), ("W2", C.c_void_p)]
+
+
 SIGNATURES = {
     "spk_abi_version": (_I32, []),
     "spk_last_error": (C.c_char_p, []),
@@ -187,6 +195,8 @@ SIGNATURES = {
     "spk_residual_norm_fwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
     "spk_residual_norm_bwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP]),
     "spk_mask_from_index": (_I32, [_VP, _I64, _VP, _I64, _VP]),
+    "spk_attn_weights_fwd": (_I32, [_VP, _VP]),
+    "spk_attn_weights_bwd": (_I32, [_VP, _VP]),
     "spk_inner_product_workspace_bytes": (_I64, []),
     "spk_inner_product": (_I32, [_VP, _VP, _I64, _VP, _VP, _I32, _VP]),
     "spk_margin_loss_partials": (_I64, [_I64]),

@@ -444,6 +444,36 @@ int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t
 int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream) {
     return mask_from_index(reinterpret_cast<const long long*>(idx), n_idx, mask, n_rows, (cudaStream_t)stream);
 }
+static int attn_weights_of(const spk_attn_weights_args* p, AttnWeightsArgs& w, bool bwd) {
+    if (!p || p->n_heads < 1 || p->n_heads > 4 || p->F < 1 || p->Rd < 1 || p->D < 1 || (p->mode != 0 && p->mode != 1) ||
+        !p->W0 || !p->W1 || (p->mode == 1 && !p->W2)) { set_error("attn_weights: bad arguments"); return 1; }
+    for (int h = 0; h < 4; ++h) {
+        w.a[h] = h < p->n_heads ? p->a[h] : nullptr; w.a2[h] = h < p->n_heads ? p->a2[h] : nullptr;
+        w.da[h] = h < p->n_heads ? p->da[h] : nullptr; w.da2[h] = h < p->n_heads ? p->da2[h] : nullptr;
+        if (h < p->n_heads && (!w.a[h] || !w.a2[h] || (bwd && (!w.da[h] || !w.da2[h])))) { set_error("attn_weights: null parameter pointer"); return 1; }
+    }
+    w.H = p->n_heads; w.F = p->F; w.Rd = p->Rd; w.D = p->D; w.mode = p->mode;
+    w.Dp = p->d_pad; w.Dt = p->n_heads * p->d_pad; w.Wd = p->width; w.Fp = p->f_pad; w.LZ = p->lz;
+    w.W0 = p->W0; w.ld0 = p->ld0; w.W1 = p->W1; w.ld1 = p->ld1; w.W2 = p->W2;
+    if (p->mode == 0 && (p->d_pad < p->D || p->width < w.Dt + p->n_heads || p->ld0 < 2L * p->width || p->ld1 < p->width)) {
+        set_error("attn_weights: geometry / leading dimensions too small"); return 1;
+    }
+    if (p->mode == 1 && (p->f_pad < p->F || p->lz < 2 * p->f_pad + p->Rd || p->n_heads > 2)) {
+        set_error("attn_weights: aggregate-then-project geometry"); return 1;
+    }
+    return 0;
+}
+int spk_attn_weights_fwd(const spk_attn_weights_args* p, spk_stream_t stream) {
+    AttnWeightsArgs w;
+    if (int rc = attn_weights_of(p, w, false)) return rc;
+    return launch_attn_weights_fwd(w, (cudaStream_t)stream);
+}
+int spk_attn_weights_bwd(const spk_attn_weights_args* p, spk_stream_t stream) {
+    AttnWeightsArgs w;
+    if (int rc = attn_weights_of(p, w, true)) return rc;
+    return launch_attn_weights_bwd(w, (cudaStream_t)stream);
+}
+
 int64_t spk_inner_product_workspace_bytes(void) { return inner_product_workspace_bytes(); }
 int spk_inner_product(const float* a, const float* b, int64_t n, void* workspace, float* out, int32_t accumulate,
                       spk_stream_t stream) {

@@ -44,8 +44,78 @@ class Geometry:
         return _lib.Geom(self.H, self.D, self.Dp, self.Wd)
 
 
+class AttnWeightsFn(torch.autograd.Function):
+    """(a_0 .. a_{H-1}, a_2,0 .. a_2,{H-1}) -> the extended weight matrices of one head group, on the library's assembly
+    kernels (spk_attn_weights_fwd / _bwd): mode 0 -> (Wn, Wr), mode 1 -> (Wa, V, V3). Same values and gradients as the
+    torch formulation below (`_extended_weights_torch`, `_agg_weights_torch`: kept for CPU tensors / fp64 checks)."""
+
+    @staticmethod
+    def _args(mode, dims, params):
+        H = len(params) // 2
+        w = _lib.AttnWeightsArgs()
+        for h in range(H):
+            w.a[h] = params[h].data_ptr(); w.a2[h] = params[H + h].data_ptr()
+        w.n_heads = H; w.F, w.Rd, w.D = dims["F"], dims["Rd"], dims["D"]
+        w.mode = mode
+        if mode == 0:
+            w.d_pad, w.width = dims["Dp"], dims["Wd"]
+        else:
+            w.f_pad, w.lz = dims["Fp"], dims["LZ"]
+        return w
+
+    @staticmethod
+    def forward(ctx, mode, dims, *params):
+        params = tuple(p.contiguous() for p in params)
+        dev = params[0].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        F, Rd, D, H = dims["F"], dims["Rd"], dims["D"], len(params) // 2
+        if mode == 0:
+            outs = (torch.empty(F, 2 * dims["Wd"], **f32), torch.empty(Rd, dims["Wd"], **f32))
+        else:
+            outs = (torch.empty(H, dims["LZ"], D, **f32), torch.empty(F, 4, **f32), torch.empty(Rd, 4, **f32))
+        w = AttnWeightsFn._args(mode, dims, params)
+        w.W0 = outs[0].data_ptr(); w.ld0 = outs[0].stride(0) if mode == 0 else D
+        w.W1 = outs[1].data_ptr(); w.ld1 = outs[1].stride(0)
+        if mode == 1:
+            w.W2 = outs[2].data_ptr()
+        _lib.check(_lib.load().spk_attn_weights_fwd(C.byref(w), _lib.stream_ptr()), "attn_weights_fwd")
+        ctx.save_for_backward(*params)
+        ctx.mode, ctx.dims = mode, dims
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        params = ctx.saved_tensors
+        mode, dims = ctx.mode, ctx.dims
+        dev = params[0].device
+        F, Rd, D, H = dims["F"], dims["Rd"], dims["D"], len(params) // 2
+        shapes = ((F, 2 * dims["Wd"]), (Rd, dims["Wd"])) if mode == 0 else ((H, dims["LZ"], D), (F, 4), (Rd, 4))
+        g = [torch.zeros(s, dtype=torch.float32, device=dev) if x is None else x.contiguous() for x, s in zip(grads, shapes)]
+        dparams = [torch.empty_like(p) for p in params]
+        w = AttnWeightsFn._args(mode, dims, params)
+        for h in range(H):
+            w.da[h] = dparams[h].data_ptr(); w.da2[h] = dparams[H + h].data_ptr()
+        w.W0 = g[0].data_ptr(); w.ld0 = g[0].stride(0) if mode == 0 else D
+        w.W1 = g[1].data_ptr(); w.ld1 = g[1].stride(0)
+        if mode == 1:
+            w.W2 = g[2].data_ptr()
+        _lib.check(_lib.load().spk_attn_weights_bwd(C.byref(w), _lib.stream_ptr()), "attn_weights_bwd")
+        return (None, None) + tuple(dparams)
+
+
+def _on_library(tensors):
+    return all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+
+
 def extended_weights(a_list, a2_list, in_features, geom):
     """a_list[h]: [D, 2F+Rd], a2_list[h]: [1, D] (GAT/layers.py:100-105) -> Wn [F, 2Wd], Wr [Rd, Wd]."""
+    if _on_library(list(a_list) + list(a2_list)):
+        dims = dict(F=in_features, Rd=a_list[0].shape[1] - 2 * in_features, D=geom.D, Dp=geom.Dp, Wd=geom.Wd)
+        return AttnWeightsFn.apply(0, dims, *a_list, *a2_list)
+    return _extended_weights_torch(a_list, a2_list, in_features, geom)
+
+
+def _extended_weights_torch(a_list, a2_list, in_features, geom):
     F = in_features
     a0 = a_list[0]
     rd = a0.shape[1] - 2 * F
@@ -599,7 +669,14 @@ def agg_weights(a_list, a2_list, geom):
          Wa [H, LZ, D]  a_h^T with zero rows at the pad positions of Zn_h = [sw x_i | sum w x_j | sum w r_k]
          V  [F, 4]      (A2^T a_2^T)_0, (..)_1, (A1^T a_2^T)_0, (..)_1      score vectors of X~
          V3 [Rd, 4]     (A3^T a_2^T)_0, (..)_1, 0, 0                        score vectors of Rel~
-    Differentiable torch ops on these tiny tensors, so autograd chains back to a and a_2."""
+    On the library's assembly kernels for CUDA fp32 parameters (AttnWeightsFn), else differentiable torch ops."""
+    if _on_library(list(a_list) + list(a2_list)):
+        dims = dict(F=geom.F, Rd=geom.Rd, D=geom.D, Fp=geom.Fp, LZ=geom.LZ)
+        return AttnWeightsFn.apply(1, dims, *a_list, *a2_list)
+    return _agg_weights_torch(a_list, a2_list, geom)
+
+
+def _agg_weights_torch(a_list, a2_list, geom):
     F, Rd, Fp = geom.F, geom.Rd, geom.Fp
     a0 = a_list[0]
     Wa = a0.new_zeros(geom.H, geom.LZ, geom.D)

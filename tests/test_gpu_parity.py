@@ -192,6 +192,29 @@ def test_gemm_tn_tc_padded_view():
     assert rel_l2(c, x.double().cpu().t() @ gp.double().cpu()) < 2e-5
 
 
+@pytest.mark.parametrize("H,F,Rd,D", [(1, 12, 12, 16), (2, 50, 50, 100), (3, 10, 6, 7), (4, 200, 200, 50), (1, 200, 200, 200)])
+def test_attn_weights_kernels_match_torch_formulation(H, F, Rd, D):
+    """spk_attn_weights_fwd / _bwd (the extended weight matrices and the gradients back to a, a_2) against the
+    differentiable torch formulation they replace (GAT/layers.py:100-105 parameters), both layouts."""
+    from recon_b200 import functional as SF
+    g = torch.Generator().manual_seed(H * 1000 + F + D)
+    a = [torch.randn(D, 2 * F + Rd, generator=g).to(dev()).requires_grad_(True) for _ in range(H)]
+    a2 = [torch.randn(1, D, generator=g).to(dev()).requires_grad_(True) for _ in range(H)]
+    cases = [("proj", lambda fn: fn(a, a2, F, SF.Geometry(H, D)), SF.extended_weights, SF._extended_weights_torch)]
+    if H <= SF.AGG_MAX_HEADS and SF.AggGeometry.supported(H, F, Rd):
+        ag = SF.AggGeometry(H, F, Rd, D)
+        cases.append(("agg", lambda fn: fn(a, a2, ag), SF.agg_weights, SF._agg_weights_torch))
+    for name, call, lib_fn, torch_fn in cases:
+        outs, refs = call(lib_fn), call(torch_fn)
+        seeds = [torch.randn(o.shape, generator=g).to(dev()) for o in refs]
+        for o, r in zip(outs, refs):
+            assert o.shape == r.shape and rel_l2(o, r.double().cpu()) < 1e-6, name   # data movement + one dot per column
+        got = torch.autograd.grad(outs, a + a2, seeds)
+        want = torch.autograd.grad(refs, a + a2, seeds)
+        for x, y in zip(got, want):
+            assert rel_l2(x, y.double().cpu()) < 2e-6, name
+
+
 # ---- stand-alone op and layer ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["spmm_f1", "spmm_f7"])
 def test_special_spmm_golden(name):
