@@ -280,7 +280,9 @@ int spk_residual_norm_fwd(const float* ew, int64_t lde, const float* x2, int64_t
 int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t ldo, const float* mask,
                           const float* inv_norm, float* dew, int64_t lde, float* dx2, int64_t ldx,
                           int64_t n_rows, int32_t width, spk_stream_t stream);
-int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream);
+/* idx may hold negative (from-the-end) indices; one outside [-n_rows, n_rows) ORs 2 into *flag (nullable): the same sticky
+ * flag word as `nanflag`, read back once per forward (1: the reference's isnan assertion, 2: its IndexError) */
+int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, int32_t* flag, spk_stream_t stream);
 /* out[0] (+)= <a, b> over n contiguous floats (16-byte aligned), deterministic (fixed chunking, fp64 across threads):
  * the linear probe loss <out_entity, G_e> + <out_relation, G_r> of SURVEY.md 8d (the reference's step writes it as
  * (out * G).sum()). workspace: spk_inner_product_workspace_bytes() bytes of device memory. */

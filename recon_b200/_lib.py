@@ -194,7 +194,7 @@ SIGNATURES = {
     "spk_rownorm": (_I32, [_VP, _I64, _VP, _I64, _I64, _I32, _VP]),
     "spk_residual_norm_fwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _I64, _VP, _I64, _I32, _VP]),
     "spk_residual_norm_bwd": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP, _VP, _I64, _VP, _I64, _I64, _I32, _VP]),
-    "spk_mask_from_index": (_I32, [_VP, _I64, _VP, _I64, _VP]),
+    "spk_mask_from_index": (_I32, [_VP, _I64, _VP, _I64, _VP, _VP]),
     "spk_attn_weights_fwd": (_I32, [_VP, _VP]),
     "spk_attn_weights_bwd": (_I32, [_VP, _VP]),
     "spk_inner_product_workspace_bytes": (_I64, []),

@@ -441,8 +441,8 @@ int spk_residual_norm_bwd(const float* g, int64_t ldg, const float* out, int64_t
                           int32_t width, spk_stream_t stream) {
     return residual_norm_bwd(g, ldg, out, ldo, mask, inv_norm, dew, lde, dx2, ldx, n_rows, width, (cudaStream_t)stream);
 }
-int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, spk_stream_t stream) {
-    return mask_from_index(reinterpret_cast<const long long*>(idx), n_idx, mask, n_rows, (cudaStream_t)stream);
+int spk_mask_from_index(const int64_t* idx, int64_t n_idx, float* mask, int64_t n_rows, int32_t* flag, spk_stream_t stream) {
+    return mask_from_index(reinterpret_cast<const long long*>(idx), n_idx, mask, n_rows, flag, (cudaStream_t)stream);
 }
 static int attn_weights_of(const spk_attn_weights_args* p, AttnWeightsArgs& w, bool bwd) {
     if (!p || p->n_heads < 1 || p->n_heads > 4 || p->F < 1 || p->Rd < 1 || p->D < 1 || (p->mode != 0 && p->mode != 1) ||

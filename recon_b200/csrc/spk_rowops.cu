@@ -101,11 +101,16 @@ residual_norm_bwd_kernel(const float* __restrict__ g, long ldg, const float* __r
     }
 }
 
-__global__ void mask_from_index_kernel(const long long* __restrict__ idx, long n_idx, float* __restrict__ mask, long n_rows) {
+// negative indices count from the end (the reference indexes a tensor with them); an index outside [-n_rows, n_rows) sets
+// bit 1 of *flag (the reference raises IndexError there) instead of costing the caller a min / max read-back per step
+__global__ void mask_from_index_kernel(const long long* __restrict__ idx, long n_idx, float* __restrict__ mask, long n_rows,
+                                       int* __restrict__ flag) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_idx) return;
-    const long long r = idx[i];
+    long long r = idx[i];
+    if (r < 0) r += n_rows;
     if (r >= 0 && r < n_rows) mask[r] = 1.0f;        // idempotent store: duplicates are harmless
+    else if (flag) atomicOr(flag, 2);
 }
 
 // <a, b> over n contiguous floats, deterministic: every block sums a fixed contiguous chunk (float4 loads, fp32 per thread,
@@ -190,9 +195,9 @@ int residual_norm_bwd(const float* g, long ldg, const float* out, long ldo, cons
     residual_norm_bwd_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, s>>>(g, ldg, out, ldo, mask, inv_norm, dew, lde, dx2, ldx, n_rows, width);
     return check_launch("residual_norm_bwd");
 }
-int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, cudaStream_t s) {
+int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, int* flag, cudaStream_t s) {
     if (n_idx <= 0) return 0;
-    mask_from_index_kernel<<<(unsigned)((n_idx + 255) / 256), 256, 0, s>>>(idx, n_idx, mask, n_rows);
+    mask_from_index_kernel<<<(unsigned)((n_idx + 255) / 256), 256, 0, s>>>(idx, n_idx, mask, n_rows, flag);
     return check_launch("mask_from_index");
 }
 }  // namespace spk

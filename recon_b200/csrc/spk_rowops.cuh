@@ -6,7 +6,7 @@ int residual_norm(const float* ew, long lde, const float* x2, long ldx, const fl
                   float* inv_norm, long n_rows, int width, cudaStream_t s);
 int residual_norm_bwd(const float* g, long ldg, const float* out, long ldo, const float* mask, const float* inv_norm,
                       float* dew, long lde, float* dx2, long ldx, long n_rows, int width, cudaStream_t s);
-int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, cudaStream_t s);
+int mask_from_index(const long long* idx, long n_idx, float* mask, long n_rows, int* flag, cudaStream_t s);
 // extended weight assembly (spk_weights.cu)
 struct AttnWeightsArgs {
     const float* a[4]; const float* a2[4];

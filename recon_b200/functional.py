@@ -506,7 +506,7 @@ class AttentionGroupFn(torch.autograd.Function):
             k_elu = bool(apply_elu) and n > 0                    # (a rank may own no rows at all: then every row is a ghost row)
             out, den, sw = edge_attn_forward(graph, P1, P2, P3, geom, alpha, k_elu, mask_csr, nanflag, elu_rows=n if k_elu else 0)
             _ghost_combine(ghost, out, den, sw, n, geom.H)
-            nanflag.add_(torch.isnan(out[n:]).any().to(torch.int32))
+            nanflag.bitwise_or_(torch.isnan(out[n:]).any().to(torch.int32))
             if apply_elu and out.shape[0] > n:
                 tail = out[n:]
                 _lib.check(_lib.load().spk_elu_inplace(_lib.ptr(tail), tail.stride(0), tail.shape[0], tail.shape[1],
@@ -759,7 +759,7 @@ class AggGroupFn(torch.autograd.Function):
         for h in range(H):                                  # a.mm(.) of layers.py:137 on the aggregated rows (+ ELU 175)
             gemm_nn(Z[:, h * LZ:(h + 1) * LZ], Wa[h], out=out[:, h * D:(h + 1) * D], act=int(apply_elu))
         if ghost is not None:
-            nanflag.add_(torch.isnan(out[n_loc:]).any().to(torch.int32))
+            nanflag.bitwise_or_(torch.isnan(out[n_loc:]).any().to(torch.int32))
             out[ghost.mine_local] = out[n_loc:][ghost.mine]  # the owner's copy of a hub row takes the combined result
         ctx.save_for_backward(X, Rel, Wa, V, V3, Xt, Rt, Z, out, den, sw, Xc)
         ctx.graph, ctx.geom, ctx.alpha, ctx.apply_elu, ctx.mask_csr = graph, geom, alpha, apply_elu, mask_csr
@@ -984,16 +984,24 @@ def rownorm(x):
     return y
 
 
-def mask_from_index(idx, n_rows, device):
-    """mask[unique(idx)] = 1 (models.py:167-173); duplicates are harmless so no unique() is needed."""
+def mask_from_index(idx, n_rows, device, flag=None):
+    """mask[unique(idx)] = 1 (models.py:167-173); duplicates are harmless so no unique() is needed. An index outside
+    [-n_rows, n_rows) is the reference's IndexError: raised here for host tensors (checked on the host, no device sync);
+    for device tensors the kernel ORs 2 into `flag` (the model's sticky flag word, read once per forward by check_nanflag),
+    or, without `flag`, into a private word that is read back here."""
     mask = torch.zeros(n_rows, dtype=torch.float32, device=device)
-    idx = idx.to(device=device, dtype=torch.int64).contiguous()
-    if idx.numel():
+    if idx.numel() and not idx.is_cuda:
         if int(idx.min()) < -n_rows or int(idx.max()) >= n_rows:
             raise IndexError("batch_entities index out of range")
-        idx = torch.where(idx < 0, idx + n_rows, idx)
-        _lib.check(_lib.load().spk_mask_from_index(_lib.ptr(idx), idx.numel(), _lib.ptr(mask), n_rows,
+    idx = idx.to(device=device, dtype=torch.int64).contiguous()
+    if idx.numel():
+        own = flag is None
+        if own:
+            flag = torch.zeros(1, dtype=torch.int32, device=device)
+        _lib.check(_lib.load().spk_mask_from_index(_lib.ptr(idx), idx.numel(), _lib.ptr(mask), n_rows, _lib.ptr(flag),
                                                    _lib.stream_ptr()), "mask_from_index")
+        if own and int(flag.item()) & 2:
+            raise IndexError("batch_entities index out of range")
     return mask
 
 

@@ -64,10 +64,14 @@ class SpecialSpmmFinal(nn.Module):
 
 
 def check_nanflag(nanflag):
-    """The reference asserts `not isnan` at layers.py:147,167,172; same AssertionError here, one sync."""
-    if int(nanflag.item()) != 0:
+    """The reference asserts `not isnan` at layers.py:147,167,172; same AssertionError here, one sync per forward.
+    Bit 1 of the word is the batch-index range check of models.py:167-173 (IndexError in the reference)."""
+    v = int(nanflag.item())
+    if v != 0:
         nanflag.zero_()
-        raise AssertionError("NaN in attention coefficients / aggregated features (reference: GAT/layers.py:147,167,172)")
+        if v & 1:
+            raise AssertionError("NaN in attention coefficients / aggregated features (reference: GAT/layers.py:147,167,172)")
+        raise IndexError("batch_entities index out of range")
 
 
 def edge_dropout_mask(p, n_heads, n_edges, device):

@@ -176,7 +176,7 @@ class SpKBGATModified(nn.Module):
         out_entity_1, out_relation_1 = self.sparse_gat_1(
             None, entity_embeddings, relation_embeddings, None, None, None, None, None,
             graph=graph, dropout_masks=dropout_masks, nanflag=nanflag)
-        mask = SF.mask_from_index(torch.as_tensor(batch_entities), entity_embeddings.shape[0], dev)   # 167-173
+        mask = SF.mask_from_index(torch.as_tensor(batch_entities), entity_embeddings.shape[0], dev, flag=nanflag)   # 167-173
         entities_upgraded = SF.matmul(entity_embeddings, self.W_entities, getattr(graph, "dist", None))  # 175
         out_entity_1 = SF.ResidualNormFn.apply(entities_upgraded, out_entity_1, mask)                 # 176-179
         check_nanflag(nanflag)

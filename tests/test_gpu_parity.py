@@ -131,6 +131,28 @@ def test_gemm_nn(m, k, n, gemm_path):
     assert rel_l2(c2, c0.double() + a.double() @ b.double()) < tol
 
 
+def test_batch_index_range_check_without_host_sync():
+    """models.py:167-173 indexes the mask with the batch entities: out-of-range -> IndexError, negative = from the end. Device
+    index tensors are checked by the kernel through the model's sticky flag word (no min / max read-back per step)."""
+    from recon_b200 import SpKBGATModified
+    from recon_b200 import functional as SF
+    from recon_b200.synth import make_kg
+    n, r = 60, 5
+    edge, etype, _ = make_kg(n, 400, r, seed=2)
+    model = SpKBGATModified(torch.randn(n, 8), torch.randn(r, 8), [6, 12], [6, 12], 0.0, 0.2, [2, 2], None).to(dev())
+    for bad in (torch.tensor([0, 3, n]), torch.tensor([0, -n - 1])):
+        with pytest.raises(IndexError):
+            model(None, bad.to(dev()), (edge, etype), None)                 # device tensor: flagged by the kernel
+        with pytest.raises(IndexError):
+            model(None, bad, (edge, etype), None)                           # host tensor: checked on the host
+    _, _, mask = model(None, torch.tensor([1, -1, 1], device=dev()), (edge, etype), None)   # the flag word is clean again
+    want = torch.zeros(n); want[1] = 1.0; want[n - 1] = 1.0
+    assert torch.equal(mask.cpu(), want)
+    with pytest.raises(IndexError):
+        SF.mask_from_index(torch.tensor([n + 5], device=dev()), n, dev())   # stand-alone call: private flag word
+    assert torch.equal(SF.mask_from_index(torch.tensor([-2], device=dev()), n, dev()).cpu().nonzero().flatten(), torch.tensor([n - 2]))
+
+
 def test_gemm_nn_partial_last_tile_keeps_every_update():
     """157 M tiles on 148 persistent CTAs with a partial last tile: the epilogue warps whose rows lie past M used to rewrite
     their staging buffers while the previous tile's last TMA reduce-add was still reading them (lost C += rows, 30 % of runs)."""
