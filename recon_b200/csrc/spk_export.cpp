@@ -21,6 +21,9 @@
 #include <thread>
 #include <vector>
 #include <condition_variable>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <functional>
 #include <mutex>
 
@@ -389,13 +392,33 @@ int spk_pack_index_host(const int64_t* src, int64_t n, int64_t stride, int64_t l
     nt = std::max(1, std::min(nt, 64));
     if (n < (1 << 18)) nt = 1;
     std::atomic<int> bad{0};
+    // The destination is a pinned staging buffer that the copy engine reads next and the cores never read back: written
+    // with non-temporal stores (no read-for-ownership of the destination lines: a third less memory traffic per element).
+    const uint64_t span = (uint64_t)(hi - lo);
     auto work = [&](int64_t b, int64_t e) {
         int local_bad = 0;
-        for (int64_t i = b; i < e; ++i) {
+        int64_t i = b;
+#if defined(__SSE2__)
+        for (; i < e && (reinterpret_cast<uintptr_t>(dst + i) & 15); ++i) {
             const int64_t v = src[i * stride];
-            local_bad |= (v < lo) | (v >= hi);
+            local_bad |= (uint64_t)(v - lo) >= span;
             dst[i] = (int32_t)v;
         }
+        for (; i + 4 <= e; i += 4) {
+            const int64_t v0 = src[i * stride], v1 = src[(i + 1) * stride], v2 = src[(i + 2) * stride], v3 = src[(i + 3) * stride];
+            local_bad |= ((uint64_t)(v0 - lo) >= span) | ((uint64_t)(v1 - lo) >= span) | ((uint64_t)(v2 - lo) >= span) |
+                         ((uint64_t)(v3 - lo) >= span);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_set_epi32((int32_t)v3, (int32_t)v2, (int32_t)v1, (int32_t)v0));
+        }
+#endif
+        for (; i < e; ++i) {
+            const int64_t v = src[i * stride];
+            local_bad |= (uint64_t)(v - lo) >= span;
+            dst[i] = (int32_t)v;
+        }
+#if defined(__SSE2__)
+        _mm_sfence();
+#endif
         if (local_bad) bad.store(1, std::memory_order_relaxed);
     };
     if (nt == 1) work(0, n);

@@ -12,6 +12,7 @@ tensors, so autograd chains dWn, dWr back to a and a_2.
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -218,9 +219,10 @@ def _x_key(X):
 
 def _tma_operand(X):
     if _X_TABLE["key"] is not None and _X_TABLE["key"] == _x_key(X) and USE_TC:
-        t = _X_TABLE["table"]
+        t = _X_TABLE["table"]()                             # weak reference: the cache never keeps the table alive
         _X_TABLE["key"] = _X_TABLE["table"] = None          # one-shot: the table is only trusted right after it was built
-        return t[:, :X.shape[1]]
+        if t is not None:
+            return t[:, :X.shape[1]]
     return tc_friendly(X.contiguous())
 
 
@@ -724,7 +726,7 @@ class AggGroupFn(torch.autograd.Function):
             Xt = _agg_table(X, V, geom.LX, geom.Fx4)
             Xc = Xt
             Rt = _agg_table(Rel, V3, geom.LR, geom.Fr4)
-            _X_TABLE["key"], _X_TABLE["table"] = _x_key(X), Xt
+            _X_TABLE["key"], _X_TABLE["table"] = _x_key(X), weakref.ref(Xt)
         else:
             Xc, Xt = dist.gather_buffer(geom.LX, dev)
             _agg_table(X, V, geom.LX, geom.Fx4, out=Xt)

@@ -132,7 +132,7 @@ def _segment_ptr(sorted_keys, n_seg):
     return ptr
 
 
-PACK_CHUNK = int(os.environ.get("SPK_PACK_CHUNK", str(4 << 20)))      # elements per pack + copy step of the host stager
+PACK_CHUNK = int(os.environ.get("SPK_PACK_CHUNK", str(8 << 20)))      # elements per pack + copy step of the host stager
 _STAGING = {}          # device index -> {"buf": pinned int32 tensor, "event": last H2D that read it, "stream": copy stream}
 
 
