@@ -142,6 +142,21 @@ class SpKBGATModified(nn.Module):
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     # -- graph handling ------------------------------------------------------------------------
+    def _graph_key(self, adj, train_indices_nhop):
+        """identity + version + a cheap content fingerprint (first / middle / last elements, read on the host only for CPU
+        tensors) + the model's device; writes that bypass the version counter (numpy views, .data) mostly change it.
+        `model.graph_cache = False` disables caching altogether."""
+        edge_list, edge_type = adj[0], adj[1]
+        has2 = train_indices_nhop is not None and train_indices_nhop.numel() > 0
+        tensors = (edge_list, edge_type, train_indices_nhop) if has2 else (edge_list, edge_type)
+        dev = self.entity_embeddings.device
+        return (str(dev),) + tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device), _fingerprint(t)) for t in tensors)
+
+    def _graph_is_cached(self, adj, train_indices_nhop):
+        if isinstance(adj, KGraph):
+            return True
+        return bool(self.graph_cache) and self._graph_key(adj, train_indices_nhop) in self._graph_cache
+
     def prepare_graph(self, adj, train_indices_nhop=None):
         """Build (and cache by tensor identity/version) the CSR/CSC/relation layouts of an edge list."""
         if isinstance(adj, KGraph):
@@ -151,46 +166,51 @@ class SpKBGATModified(nn.Module):
         dev = self.entity_embeddings.device
         if dev.type != "cuda":
             raise RuntimeError("recon_b200.SpKBGATModified must live on a CUDA device (no CPU fallback)")
-        tensors = (edge_list, edge_type, train_indices_nhop) if has2 else (edge_list, edge_type)
-        # identity + version + a cheap content fingerprint (first / middle / last elements, read on the host only for
-        # CPU tensors) + the model's device; writes that bypass the version counter (numpy views, .data) mostly change it.
-        # `model.graph_cache = False` disables caching altogether.
-        key = (str(dev),) + tuple((t.data_ptr(), tuple(t.shape), t._version, str(t.device), _fingerprint(t)) for t in tensors)
+        key = self._graph_key(adj, train_indices_nhop)
         g = self._graph_cache.get(key) if self.graph_cache else None
         if g is None:
             nhop = train_indices_nhop if has2 else None
             with torch.cuda.device(dev):
                 g = KGraph(edge_list, edge_type, nhop, self.num_nodes, self.num_relation, device=dev)
             self._graph_cache.clear()                      # keep one graph: batches change every iteration
-            self._graph_cache[key] = g
-            g._keepalive = (edge_list, edge_type, train_indices_nhop)   # data_ptr keys stay valid while cached
+            if self.graph_cache:
+                self._graph_cache[key] = g
+                g._keepalive = (edge_list, edge_type, train_indices_nhop)   # data_ptr keys stay valid while cached
         return g
 
-    def _run(self, entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks):
+    def _run(self, entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks, entities_upgraded=None):
         with torch.cuda.device(entity_embeddings.device):
-            return self._run_on(entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks)
+            return self._run_on(entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks, entities_upgraded)
 
-    def _run_on(self, entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks):
+    def _run_on(self, entity_embeddings, relation_embeddings, batch_entities, graph, dropout_masks, entities_upgraded=None):
         dev = entity_embeddings.device
         nanflag = torch.zeros(1, dtype=torch.int32, device=dev)
         out_entity_1, out_relation_1 = self.sparse_gat_1(
             None, entity_embeddings, relation_embeddings, None, None, None, None, None,
             graph=graph, dropout_masks=dropout_masks, nanflag=nanflag)
         mask = SF.mask_from_index(torch.as_tensor(batch_entities), entity_embeddings.shape[0], dev, flag=nanflag)   # 167-173
-        entities_upgraded = SF.matmul(entity_embeddings, self.W_entities, getattr(graph, "dist", None))  # 175
+        if entities_upgraded is None:
+            entities_upgraded = SF.matmul(entity_embeddings, self.W_entities, getattr(graph, "dist", None))  # 175
         out_entity_1 = SF.ResidualNormFn.apply(entities_upgraded, out_entity_1, mask)                 # 176-179
         check_nanflag(nanflag)
         return out_entity_1, out_relation_1, mask
 
     def forward(self, Corpus_, batch_entities, adj, train_indices_nhop, dropout_masks=None):
-        graph = self.prepare_graph(adj, train_indices_nhop)
+        if self.entity_embeddings.device.type != "cuda":
+            raise RuntimeError("recon_b200.SpKBGATModified must live on a CUDA device (no CPU fallback)")
         # models.py:160-161 -- the parameter itself is overwritten with its row-normalised value
         # (rebinds .data to a fresh tensor like the reference does, so a tensor the caller shares with the Parameter and
         # anything an earlier forward saved for backward are left untouched)
+        pre = None
         with torch.cuda.device(self.entity_embeddings.device):
             self.entity_embeddings.data = SF.rownorm(self.entity_embeddings.data)
+            if not self._graph_is_cached(adj, train_indices_nhop):
+                # the layouts are about to be built (host tensors: pack + H2D, the GPU idles meanwhile): queue the one
+                # product of the forward that does not need the graph, entity_embeddings.mm(W_entities) (models.py:175)
+                pre = SF.matmul(self.entity_embeddings, self.W_entities, None)
+        graph = self.prepare_graph(adj, train_indices_nhop)
         out_entity_1, out_relation_1, mask = self._run(self.entity_embeddings, self.relation_embeddings,
-                                                       batch_entities, graph, dropout_masks)
+                                                       batch_entities, graph, dropout_masks, pre)
         self.final_entity_embeddings.data = out_entity_1.data                                         # 181
         self.final_relation_embeddings.data = out_relation_1.data                                     # 183
         return out_entity_1, out_relation_1, mask
