@@ -38,6 +38,20 @@ def test_struct_sizes_match_header_layout():
     assert C.sizeof(_lib.EdgeFwdArgs) == 17 * 8 + 16 + C.sizeof(_lib.Geom) + C.sizeof(_lib.HubTasks)
     assert C.sizeof(_lib.EdgeBwdRowsArgs) == 21 * 8 + 16 + C.sizeof(_lib.Geom) + C.sizeof(_lib.HubTasks)
     assert C.sizeof(_lib.SegGatherArgs) == 8 * 8 + 8 + C.sizeof(_lib.Geom) + C.sizeof(_lib.HubTasks)
+    assert C.sizeof(_lib.AttnWeightsArgs) == 16 * 8 + 10 * 4 + 5 * 8       # spk_attn_weights_args: 16 pointers, 10 ints, W0/ld0/W1/ld1/W2
+
+
+def test_attn_weights_argument_checks_without_gpu():
+    """spk_attn_weights_* validate their argument block before any device work (no GPU needed for the error paths)."""
+    import ctypes as C
+    from recon_b200 import _lib
+    lib = _lib.load()
+    w = _lib.AttnWeightsArgs()
+    w.n_heads, w.F, w.Rd, w.D, w.mode = 5, 4, 4, 4, 0                      # more than 4 heads
+    assert lib.spk_attn_weights_fwd(C.byref(w), None) != 0
+    assert b"attn_weights" in lib.spk_last_error()
+    w.n_heads, w.mode = 1, 7                                               # unknown mode
+    assert lib.spk_attn_weights_bwd(C.byref(w), None) != 0
 
 
 def test_product_never_imports_oracle():
